@@ -1,0 +1,5 @@
+from .gaussian import CEM, PGPE, SNES, XNES, GaussianSearchAlgorithm
+from .searchalgorithm import LazyReporter, LazyStatusDict, SearchAlgorithm, SinglePopulationAlgorithmMixin
+
+__all__ = ["PGPE", "SNES", "CEM", "XNES", "GaussianSearchAlgorithm", "SearchAlgorithm", "LazyReporter", "LazyStatusDict",
+           "SinglePopulationAlgorithmMixin"]

@@ -1,0 +1,287 @@
+"""PGPE / SNES / CEM / XNES: search algorithms driven by a Gaussian search distribution (mirrors
+evotorch.algorithms.distributed.gaussian, gaussian.py:35-1405: same constructor arguments, defaults and status keys).
+
+One generation, as in the reference (gaussian.py:351-367): the gradient is computed from the population stored by the
+PREVIOUS step, the distribution is updated, then a fresh population is sampled into the same buffers and evaluated.
+For a CUDA float32 problem that is five kernel groups per generation and no host synchronisation:
+
+    K3 rank -> K4 weighted column reduction -> K5 mu step -> K5 sigma step -> K1+K2 fused sample/evaluate
+
+`distributed=True` shards the population over the ranks of torch.distributed (see ..distributed) instead of Ray actors.
+"""
+
+from __future__ import annotations
+
+import math
+from copy import deepcopy
+from typing import Optional
+
+import torch
+
+from .. import ops
+from ..core import Problem, SolutionBatch
+from ..distributed import world
+from ..distributions import Distribution, ExpGaussian, ExpSeparableGaussian, SeparableGaussian, SymmetricSeparableGaussian
+from ..optimizers import get_optimizer_class
+from ..tools.misc import modify_tensor, to_stdev_init
+from .searchalgorithm import SearchAlgorithm, SinglePopulationAlgorithmMixin
+
+
+class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
+    """Base class of the Gaussian-distribution searchers (gaussian.py:35-501)."""
+
+    DISTRIBUTION_TYPE = NotImplemented
+    DISTRIBUTION_PARAMS = NotImplemented
+
+    def __init__(self, problem: Problem, *, popsize: int, center_learning_rate: float, stdev_learning_rate: float,
+                 stdev_init=None, radius_init=None, num_interactions: Optional[int] = None, popsize_max: Optional[int] = None,
+                 optimizer=None, optimizer_config: Optional[dict] = None, ranking_method: Optional[str] = None, center_init=None,
+                 stdev_min=None, stdev_max=None, stdev_max_change=None, obj_index: Optional[int] = None, distributed: bool = False,
+                 popsize_weighted_grad_avg: Optional[bool] = None, ensure_even_popsize: bool = False):
+        problem.ensure_numeric()
+        problem.ensure_unbounded()
+        SearchAlgorithm.__init__(self, problem, center=self._get_mu, stdev=self._get_sigma, mean_eval=self._get_mean_eval)
+        if num_interactions is not None or popsize_max is not None:
+            raise NotImplementedError("adaptive population size (num_interactions / popsize_max) is an RL-only feature and out of scope")
+        self._ensure_even_popsize = bool(ensure_even_popsize)
+        if self._ensure_even_popsize and (int(popsize) % 2) != 0 and not distributed:
+            raise ValueError(f"`popsize` was expected as an even number. However, the received `popsize` is {popsize}.")
+
+        if center_init is None:
+            mu = problem.generate_values(1).reshape(-1)
+        else:
+            mu = problem.ensure_tensor_length_and_dtype(center_init, allow_scalar=False, about="center_init").clone()
+        stdev_init = to_stdev_init(solution_length=problem.solution_length, stdev_init=stdev_init, radius_init=radius_init)
+        sigma = problem.ensure_tensor_length_and_dtype(stdev_init, about="stdev_init", allow_scalar=False).clone()
+
+        dist_params = deepcopy(self.DISTRIBUTION_PARAMS) if self.DISTRIBUTION_PARAMS is not None else {}
+        dist_params.update({"mu": mu, "sigma": sigma})
+        self._distribution: Distribution = self.DISTRIBUTION_TYPE(dist_params, dtype=problem.dtype, device=problem.device)
+
+        self._popsize = int(popsize)
+        self._center_learning_rate = float(center_learning_rate)
+        self._stdev_learning_rate = float(stdev_learning_rate)
+        self._optimizer = self._initialize_optimizer(self._center_learning_rate, optimizer, optimizer_config)
+        self._ranking_method = None if ranking_method is None else str(ranking_method)
+
+        def bound(x, about):
+            return None if x is None else problem.ensure_tensor_length_and_dtype(x, about=about, allow_scalar=True)
+
+        self._stdev_min = bound(stdev_min, "stdev_min")
+        self._stdev_max = bound(stdev_max, "stdev_max")
+        self._stdev_max_change = bound(stdev_max_change, "stdev_max_change")
+        self._obj_index = problem.normalize_obj_index(obj_index)
+
+        # `distributed=True` shards the population over torch.distributed ranks (the reference needs Ray actors for this)
+        self._distributed = bool(distributed) and world()[1] > 1
+        self._step = self._step_distributed if self._distributed else self._step_non_distributed
+        if popsize_weighted_grad_avg is not None and not distributed:
+            raise ValueError("The argument `popsize_weighted_grad_avg` can only be used in distributed mode.")
+
+        self._mean_eval = None
+        self._population: Optional[SolutionBatch] = None
+        self._first_iter = True
+        SinglePopulationAlgorithmMixin.__init__(self, exclude="mean_eval", enable=(not self._distributed))
+
+    def _initialize_optimizer(self, learning_rate: float, optimizer=None, optimizer_config: Optional[dict] = None):
+        if optimizer is None:
+            return None
+        if isinstance(optimizer, str):
+            cls = get_optimizer_class(optimizer, optimizer_config)
+            return cls(stepsize=float(learning_rate), dtype=self._distribution.dtype, solution_length=self._distribution.solution_length,
+                       device=self._distribution.device)
+        return optimizer
+
+    # ------------------------------------------------------------------ generations
+    def _fill_and_eval_pop(self):
+        if self._population is None:
+            self._population = SolutionBatch(self.problem, popsize=self._popsize, device=self._distribution.device, empty=True)
+        self.problem.sample_and_evaluate(self._distribution, self._population)
+
+    def _step_non_distributed(self):
+        """gaussian.py:274-367."""
+        if self._first_iter:
+            self._fill_and_eval_pop()
+            self._first_iter = False
+            return
+        samples = self._population.access_values(keep_evals=True)
+        fitnesses = self._population.access_evals()[:, self._obj_index]
+        gradients = self._distribution.compute_gradients(samples, fitnesses, objective_sense=self.problem.senses[self._obj_index],
+                                                         ranking_method=self._ranking_method)
+        self._update_distribution(gradients)
+        self._fill_and_eval_pop()
+
+    def _step_distributed(self):
+        """Every rank: sample/evaluate its shard, global ranking, all-reduced gradients, replicated update
+        (replaces gaussian.py:199-272)."""
+        fetched = self.problem.sample_and_compute_gradients(self._distribution, self._popsize, obj_index=self._obj_index,
+                                                            ranking_method=self._ranking_method,
+                                                            ensure_even_popsize=self._ensure_even_popsize)
+        self._update_distribution(fetched[0]["gradients"])
+        self._mean_eval = fetched[0]["mean_eval"]
+
+    # ------------------------------------------------------------------ distribution update (K5)
+    def _update_distribution(self, gradients: dict):
+        """gaussian.py:369-419: follow the gradients, then clamp sigma against its pre-update value."""
+        dist = self._distribution
+        separable = isinstance(dist, SeparableGaussian)
+        if separable and ops.uses_kernels(dist.mu) and ops.uses_kernels(gradients["mu"]):
+            # two launches, in place on copies (the previous generation's tensors stay valid for whoever holds them)
+            new_mu, new_sigma = dist.mu.clone(), dist.sigma.clone()
+            gmu = gradients["mu"].contiguous()
+            if self._optimizer is not None and hasattr(self._optimizer, "ascent_into_"):
+                self._optimizer.ascent_into_(gmu, new_mu)
+            elif self._optimizer is not None:
+                new_mu += self._optimizer.ascent(gmu)
+            else:
+                ops.axpy_(new_mu, gmu, self._center_learning_rate)
+            ops.sigma_update_(new_sigma, gradients["sigma"].contiguous(), self._stdev_learning_rate,
+                              isinstance(dist, ExpSeparableGaussian), lb=self._stdev_min, ub=self._stdev_max,
+                              max_change=self._stdev_max_change)
+            self._distribution = dist.modified_copy(mu=new_mu, sigma=new_sigma)
+            return
+
+        controlled = (self._stdev_min is not None) or (self._stdev_max is not None) or (self._stdev_max_change is not None)
+        old_sigma = dist.sigma if controlled else None
+        learning_rates, optimizers = {}, {}
+        if self._optimizer is not None:
+            optimizers["mu"] = self._optimizer
+        else:
+            learning_rates["mu"] = self._center_learning_rate
+        learning_rates["sigma"] = self._stdev_learning_rate
+        updated = dist.update_parameters(gradients, learning_rates=learning_rates, optimizers=optimizers)
+        if controlled:
+            updated = updated.modified_copy(
+                sigma=modify_tensor(old_sigma, updated.sigma, lb=self._stdev_min, ub=self._stdev_max, max_change=self._stdev_max_change))
+        self._distribution = updated
+
+    # ------------------------------------------------------------------ status
+    def _get_mu(self) -> torch.Tensor:
+        return self._distribution.parameters["mu"]
+
+    def _get_sigma(self) -> torch.Tensor:
+        return self._distribution.parameters["sigma"]
+
+    def _get_mean_eval(self) -> Optional[float]:
+        if self._population is None:
+            return None if self._mean_eval is None else float(self._mean_eval)
+        return float(torch.mean(self._population.evals[:, self._obj_index]))
+
+    @property
+    def optimizer(self):
+        """The center optimizer (`None`, `ClipUp`, `Adam` or `SGD`); `optimizer.param_groups[0]["lr"]` is readable/writable."""
+        return None if self._optimizer is None else self._optimizer.contained_optimizer
+
+    @property
+    def population(self) -> Optional[SolutionBatch]:
+        """The current population (None in sharded mode, where each rank only holds its shard)."""
+        return self._population
+
+    @property
+    def obj_index(self) -> int:
+        return self._obj_index
+
+
+class PGPE(GaussianSearchAlgorithm):
+    """Policy Gradients with Parameter-based Exploration (gaussian.py:503-744): symmetric sampling, ClipUp, centered
+    ranking and stdev_max_change=0.2 by default."""
+
+    DISTRIBUTION_TYPE = NotImplemented
+    DISTRIBUTION_PARAMS = NotImplemented
+
+    def __init__(self, problem: Problem, *, popsize: int, center_learning_rate: float, stdev_learning_rate: float, stdev_init=None,
+                 radius_init=None, num_interactions: Optional[int] = None, popsize_max: Optional[int] = None, optimizer="clipup",
+                 optimizer_config: Optional[dict] = None, ranking_method: Optional[str] = "centered", center_init=None, stdev_min=None,
+                 stdev_max=None, stdev_max_change=0.2, symmetric: bool = True, obj_index: Optional[int] = None,
+                 distributed: bool = False, popsize_weighted_grad_avg: Optional[bool] = None):
+        if symmetric:
+            self.DISTRIBUTION_TYPE = SymmetricSeparableGaussian
+            divide_by = "num_directions"
+        else:
+            self.DISTRIBUTION_TYPE = SeparableGaussian
+            divide_by = "num_solutions"
+        self.DISTRIBUTION_PARAMS = {"divide_mu_grad_by": divide_by, "divide_sigma_grad_by": divide_by}
+        super().__init__(problem, popsize=popsize, center_learning_rate=center_learning_rate, stdev_learning_rate=stdev_learning_rate,
+                         stdev_init=stdev_init, radius_init=radius_init, popsize_max=popsize_max, num_interactions=num_interactions,
+                         optimizer=optimizer, optimizer_config=optimizer_config, ranking_method=ranking_method, center_init=center_init,
+                         stdev_min=stdev_min, stdev_max=stdev_max, stdev_max_change=stdev_max_change, obj_index=obj_index,
+                         distributed=distributed, popsize_weighted_grad_avg=popsize_weighted_grad_avg, ensure_even_popsize=symmetric)
+
+
+def _default_popsize(n: int) -> int:
+    return int(4 + math.floor(3 * math.log(n)))
+
+
+class SNES(GaussianSearchAlgorithm):
+    """Separable Natural Evolution Strategies (gaussian.py:746-984): popsize 4+floor(3 ln n), lr_sigma 0.2(3+ln n)/sqrt(n)."""
+
+    DISTRIBUTION_TYPE = ExpSeparableGaussian
+    DISTRIBUTION_PARAMS = None
+
+    def __init__(self, problem: Problem, *, stdev_init=None, radius_init=None, popsize: Optional[int] = None,
+                 center_learning_rate: Optional[float] = None, stdev_learning_rate: Optional[float] = None,
+                 scale_learning_rate: bool = True, num_interactions: Optional[int] = None, popsize_max: Optional[int] = None,
+                 optimizer=None, optimizer_config: Optional[dict] = None, ranking_method: Optional[str] = "nes", center_init=None,
+                 stdev_min=None, stdev_max=None, stdev_max_change=None, obj_index: Optional[int] = None, distributed: bool = False,
+                 popsize_weighted_grad_avg: Optional[bool] = None):
+        n = problem.solution_length
+        if popsize is None:
+            popsize = _default_popsize(n)
+        if center_learning_rate is None:
+            center_learning_rate = 1.0
+        default_lr = 0.2 * (3 + math.log(n)) / math.sqrt(n)
+        if stdev_learning_rate is None:
+            stdev_learning_rate = default_lr
+        else:
+            stdev_learning_rate = float(stdev_learning_rate) * (default_lr if scale_learning_rate else 1.0)
+        super().__init__(problem, popsize=popsize, center_learning_rate=center_learning_rate, stdev_learning_rate=stdev_learning_rate,
+                         stdev_init=stdev_init, radius_init=radius_init, popsize_max=popsize_max, num_interactions=num_interactions,
+                         optimizer=optimizer, optimizer_config=optimizer_config, ranking_method=ranking_method, center_init=center_init,
+                         stdev_min=stdev_min, stdev_max=stdev_max, stdev_max_change=stdev_max_change, obj_index=obj_index,
+                         distributed=distributed, popsize_weighted_grad_avg=popsize_weighted_grad_avg)
+
+
+class CEM(GaussianSearchAlgorithm):
+    """Cross-Entropy Method (gaussian.py:986-1181): the new distribution is the mean / std of the elite solutions."""
+
+    DISTRIBUTION_TYPE = SeparableGaussian
+    DISTRIBUTION_PARAMS = NotImplemented
+
+    def __init__(self, problem: Problem, *, popsize: int, parenthood_ratio: float, stdev_init=None, radius_init=None,
+                 num_interactions: Optional[int] = None, popsize_max: Optional[int] = None, center_init=None, stdev_min=None,
+                 stdev_max=None, stdev_max_change=None, obj_index: Optional[int] = None, distributed: bool = False,
+                 popsize_weighted_grad_avg: Optional[bool] = None):
+        self.DISTRIBUTION_PARAMS = {"parenthood_ratio": float(parenthood_ratio)}
+        super().__init__(problem, popsize=popsize, center_learning_rate=1.0, stdev_learning_rate=1.0, stdev_init=stdev_init,
+                         radius_init=radius_init, popsize_max=popsize_max, num_interactions=num_interactions, optimizer=None,
+                         optimizer_config=None, ranking_method=None, center_init=center_init, stdev_min=stdev_min, stdev_max=stdev_max,
+                         stdev_max_change=stdev_max_change, obj_index=obj_index, distributed=distributed,
+                         popsize_weighted_grad_avg=popsize_weighted_grad_avg)
+
+
+class XNES(GaussianSearchAlgorithm):
+    """Exponential Natural Evolution Strategies with a full covariance factor (gaussian.py:1183-1405)."""
+
+    DISTRIBUTION_TYPE = ExpGaussian
+    DISTRIBUTION_PARAMS = None
+
+    def __init__(self, problem: Problem, *, stdev_init=None, radius_init=None, popsize: Optional[int] = None,
+                 center_learning_rate: Optional[float] = None, stdev_learning_rate: Optional[float] = None,
+                 scale_learning_rate: bool = True, num_interactions: Optional[int] = None, popsize_max: Optional[int] = None,
+                 optimizer=None, optimizer_config: Optional[dict] = None, ranking_method: Optional[str] = "nes", center_init=None,
+                 obj_index: Optional[int] = None, distributed: bool = False, popsize_weighted_grad_avg: Optional[bool] = None):
+        n = problem.solution_length
+        if popsize is None:
+            popsize = _default_popsize(n)
+        if center_learning_rate is None:
+            center_learning_rate = 1.0
+        default_lr = 0.6 * (3 + math.log(n)) / (n * math.sqrt(n))
+        if stdev_learning_rate is None:
+            stdev_learning_rate = default_lr
+        else:
+            stdev_learning_rate = float(stdev_learning_rate) * (default_lr if scale_learning_rate else 1.0)
+        super().__init__(problem, popsize=popsize, center_learning_rate=center_learning_rate, stdev_learning_rate=stdev_learning_rate,
+                         stdev_init=stdev_init, radius_init=radius_init, popsize_max=popsize_max, num_interactions=num_interactions,
+                         optimizer=optimizer, optimizer_config=optimizer_config, ranking_method=ranking_method, center_init=center_init,
+                         stdev_min=None, stdev_max=None, stdev_max_change=None, obj_index=obj_index, distributed=distributed,
+                         popsize_weighted_grad_avg=popsize_weighted_grad_avg)

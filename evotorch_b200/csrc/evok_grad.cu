@@ -1,0 +1,271 @@
+// K4: utility-weighted column reductions over the population (one fused pass, two accumulators per column).
+//   S1_j = sum_r a_r eps_rj          S2_j = sum_r b_r (eps_rj^2 * c1_j - c0_j)         eps = X - mu
+// with (c1, c0) = (1/sigma, sigma) for the PGPE forms, (1/sigma^2, 1) for SNES, (1, 0) for raw moments.
+// HBM-bound: each CTA owns a column tile (128-bit loads, 4 rows in flight per thread) and a contiguous chunk of
+// rows; partial sums go to a [chunk][2][D] workspace and a second tiny kernel adds the chunks in a fixed order
+// (deterministic, no atomics).  In the symmetric form only the even ("+") rows are read.
+#include "evok_common.cuh"
+
+namespace evok {
+
+constexpr int kGradThreads = 256;
+constexpr int kGradUnroll = 4;
+constexpr int kMaxResidentCtas = 148 * 8;
+
+template <int VEC>
+struct VecF;
+template <>
+struct VecF<4> {
+  float v[4];
+};
+template <>
+struct VecF<1> {
+  float v[1];
+};
+
+template <int VEC>
+__device__ __forceinline__ VecF<VEC> load_row(const float* p) {
+  VecF<VEC> r;
+  if (VEC == 4) {
+    const float4 t = ld_stream4(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = ld_stream1(p);
+  }
+  return r;
+}
+
+// SYM: unit r = direction (rows 2r, 2r+1), else unit r = row r.  REGEN: eps = sigma * z regenerated from Philox.
+template <int VEC, int TX, bool SYM, bool REGEN>
+__global__ void __launch_bounds__(kGradThreads)
+    grad_partial_kernel(int form, const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, const float* __restrict__ mu,
+                        const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk, uint64_t unit0, uint64_t seed,
+                        uint64_t stream_id, float* __restrict__ partial) {
+  constexpr int TY = kGradThreads / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int64_t col = ((int64_t)blockIdx.x * TX + tx) * VEC;
+  const bool active = col < D;
+
+  float m[VEC], c1[VEC], c0[VEC], sg[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    const bool ok = active && (col + c < D);
+    const float s = ok ? __ldg(sigma + col + c) : 1.0f;
+    m[c] = ok ? __ldg(mu + col + c) : 0.0f;
+    sg[c] = s;
+    if (form == EVOK_GRAD_EXP) {
+      c1[c] = __fdiv_rn(1.0f, s * s);
+      c0[c] = 1.0f;
+    } else if (form == EVOK_GRAD_MOMENTS) {
+      c1[c] = 1.0f;
+      c0[c] = 0.0f;
+    } else {
+      c1[c] = __fdiv_rn(1.0f, s);
+      c0[c] = s;
+    }
+  }
+
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) s1[c] = s2[c] = 0.0f;
+
+  const int64_t r_begin = (int64_t)blockIdx.y * units_per_chunk;
+  const int64_t r_end = min(n_units, r_begin + units_per_chunk);
+
+  for (int64_t r0 = r_begin + ty; r0 < r_end; r0 += (int64_t)TY * kGradUnroll) {
+    float a[kGradUnroll], b[kGradUnroll];
+    bool need[kGradUnroll];
+    VecF<VEC> x[kGradUnroll];
+#pragma unroll
+    for (int u = 0; u < kGradUnroll; ++u) {
+      const int64_t r = r0 + (int64_t)u * TY;
+      a[u] = b[u] = 0.0f;
+      if (r < r_end) {
+        if (SYM) {
+          const float wp = __ldg(w + 2 * r), wm = __ldg(w + 2 * r + 1);
+          a[u] = 0.5f * (wp - wm);
+          b[u] = 0.5f * (wp + wm);
+        } else {
+          a[u] = b[u] = __ldg(w + r);
+        }
+      }
+      need[u] = active && (a[u] != 0.0f || b[u] != 0.0f);
+    }
+#pragma unroll
+    for (int u = 0; u < kGradUnroll; ++u) {
+      const int64_t r = r0 + (int64_t)u * TY;
+      if (need[u]) {
+        if (REGEN) {
+          if (VEC == 4) {
+            normals4(seed, stream_id, unit0 + (uint64_t)r, (uint32_t)(col >> 2), x[u].v);
+          } else {
+            float z[4];
+            normals4(seed, stream_id, unit0 + (uint64_t)r, (uint32_t)(col >> 2), z);
+            x[u].v[0] = z[col & 3];
+          }
+        } else {
+          x[u] = load_row<VEC>(X + (SYM ? 2 * r : r) * ldx + col);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGradUnroll; ++u) {
+      if (need[u]) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          const float e = REGEN ? sg[c] * x[u].v[c] : x[u].v[c] - m[c];
+          s1[c] = fmaf(a[u], e, s1[c]);
+          s2[c] = fmaf(b[u], fmaf(e * e, c1[c], -c0[c]), s2[c]);
+        }
+      }
+    }
+  }
+
+  // combine the TY row-threads of each column in a fixed order
+  __shared__ float red[TY > 1 ? TY : 1][TX][2 * VEC];
+  if (TY > 1) {
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      red[ty][tx][c] = s1[c];
+      red[ty][tx][VEC + c] = s2[c];
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        float t1 = red[0][tx][c], t2 = red[0][tx][VEC + c];
+        for (int y = 1; y < TY; ++y) {
+          t1 += red[y][tx][c];
+          t2 += red[y][tx][VEC + c];
+        }
+        s1[c] = t1;
+        s2[c] = t2;
+      }
+    }
+  }
+  if (ty == 0 && active) {
+    float* p1 = partial + ((int64_t)blockIdx.y * 2 + 0) * D + col;
+    float* p2 = partial + ((int64_t)blockIdx.y * 2 + 1) * D + col;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      if (col + c < D) {
+        p1[c] = s1[c];
+        p2[c] = s2[c];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restrict__ partial, int n_chunks, int64_t D, float scale_mu,
+                                                            float scale_sigma, float* __restrict__ out_mu, float* __restrict__ out_sigma) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  float t1 = 0.0f, t2 = 0.0f;
+  for (int c = 0; c < n_chunks; ++c) {
+    t1 += partial[((int64_t)c * 2 + 0) * D + j];
+    t2 += partial[((int64_t)c * 2 + 1) * D + j];
+  }
+  out_mu[j] = t1 * scale_mu;
+  out_sigma[j] = t2 * scale_sigma;
+}
+
+struct GradPlan {
+  int vec, tx, n_coltiles, n_chunks;
+  int64_t units_per_chunk;
+};
+
+static GradPlan plan_grad(int64_t n_units, int64_t D, bool vec_ok) {
+  GradPlan p;
+  p.vec = vec_ok ? 4 : 1;
+  const int64_t col_threads = (D + p.vec - 1) / p.vec;
+  p.tx = 32;
+  while (p.tx < kGradThreads && p.tx < col_threads) p.tx <<= 1;
+  p.n_coltiles = (int)((col_threads + p.tx - 1) / p.tx);
+  const int ty = kGradThreads / p.tx;
+  int64_t chunks = kMaxResidentCtas / 2 / p.n_coltiles;  // ~4 CTAs per SM, one wave
+  const int64_t max_useful = (n_units + (int64_t)ty * kGradUnroll - 1) / ((int64_t)ty * kGradUnroll);
+  if (chunks > max_useful) chunks = max_useful;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  p.units_per_chunk = (n_units + chunks - 1) / chunks;
+  p.n_chunks = (int)((n_units + p.units_per_chunk - 1) / p.units_per_chunk);
+  if (p.n_chunks < 1) p.n_chunks = 1;
+  return p;
+}
+
+template <int VEC, bool SYM, bool REGEN>
+static void launch_partial(const GradPlan& p, int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma,
+                           int64_t n_units, int64_t D, uint64_t unit0, uint64_t seed, uint64_t stream_id, float* partial, cudaStream_t st) {
+  dim3 grid(p.n_coltiles, p.n_chunks);
+#define EVOK_LAUNCH_TX(TXV)                                                                                                         \
+  grad_partial_kernel<VEC, TXV, SYM, REGEN><<<grid, kGradThreads, 0, st>>>(form, X, ldx, w, mu, sigma, n_units, D, p.units_per_chunk, \
+                                                                           unit0, seed, stream_id, partial)
+  switch (p.tx) {
+    case 32: EVOK_LAUNCH_TX(32); break;
+    case 64: EVOK_LAUNCH_TX(64); break;
+    case 128: EVOK_LAUNCH_TX(128); break;
+    default: EVOK_LAUNCH_TX(256); break;
+  }
+#undef EVOK_LAUNCH_TX
+}
+
+static int grad_impl(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
+                     int64_t D, bool regen, uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu,
+                     float* out_sigma, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !mu || !sigma || !out_mu || !out_sigma || !ws || (!regen && !X)) return EVOK_E_NULLPTR;
+  if (form < EVOK_GRAD_SEPARABLE || form > EVOK_GRAD_MOMENTS) return EVOK_E_BADENUM;
+  if (n_rows < 0 || D <= 0 || row0 < 0 || (!regen && ldx < D)) return EVOK_E_BADSIZE;
+  const bool sym = form == EVOK_GRAD_SYMMETRIC;
+  if (sym && ((n_rows & 1) || (row0 & 1))) return EVOK_E_ODDROWS;
+  if (ws_bytes < evok_grad_workspace_bytes(n_rows, D)) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_units = sym ? n_rows / 2 : n_rows;
+  const bool vec_ok = regen ? true : ((D % 4 == 0) && (ldx % 4 == 0) && aligned16(X));
+  // symmetric sampling keys its counters by direction; the regenerating kernel must use the same unit index
+  const uint64_t unit0 = (uint64_t)(sym ? row0 / 2 : row0);
+  GradPlan p = plan_grad(n_units, D, vec_ok);
+  float* partial = (float*)ws;
+  if (n_units == 0) {
+    cudaMemsetAsync(out_mu, 0, (size_t)D * 4, st);
+    cudaMemsetAsync(out_sigma, 0, (size_t)D * 4, st);
+    return 0;
+  }
+  if (regen) {
+    if (sym) launch_partial<4, true, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    else launch_partial<4, false, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+  } else if (vec_ok) {
+    if (sym) launch_partial<4, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    else launch_partial<4, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+  } else {
+    if (sym) launch_partial<1, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    else launch_partial<1, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+  }
+  EVOK_CHECK_LAUNCH();
+  grad_finalize_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(partial, p.n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace evok
+
+using namespace evok;
+
+extern "C" EVOK_API size_t evok_grad_workspace_bytes(int64_t n_rows, int64_t D) {
+  (void)n_rows;
+  if (D <= 0) return 256;
+  // n_chunks * n_coltiles <= kMaxResidentCtas/2 + n_coltiles and every column tile spans <= 1024 columns
+  return ((size_t)kMaxResidentCtas * 1024 + 2 * (size_t)D + 64) * sizeof(float);
+}
+
+extern "C" EVOK_API int evok_grad(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t n_rows,
+                         int64_t D, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma, void* ws, size_t ws_bytes,
+                         void* stream) {
+  return grad_impl(form, X, ldx, w, mu, sigma, 0, n_rows, D, false, 0, 0, scale_mu, scale_sigma, out_mu, out_sigma, ws, ws_bytes, stream);
+}
+
+extern "C" EVOK_API int evok_grad_regen(int form, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
+                               uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma,
+                               void* ws, size_t ws_bytes, void* stream) {
+  return grad_impl(form, nullptr, 0, w, mu, sigma, row0, n_rows, D, true, seed, stream_id, scale_mu, scale_sigma, out_mu, out_sigma, ws,
+                   ws_bytes, stream);
+}

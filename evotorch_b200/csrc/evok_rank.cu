@@ -1,0 +1,375 @@
+// K3: fitness -> utilities.  A hand-written stable LSD radix sort of (orderable fp32 key, index) pairs
+// (4 passes x 8 bits; per pass: per-tile digit histogram -> per-digit exclusive scan -> stable scatter using
+// warp match/ballot ranking), followed by a fused utility-table scatter.  N is the population size
+// (<= a few million): the whole working set lives in L2, the kernels are latency-, not bandwidth-bound.
+#include "evok_common.cuh"
+
+namespace evok {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortThreads = 256;               // 8 warps; must equal kRadix (one thread per digit)
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItemsPerThread = 8;
+constexpr int kTile = kSortThreads * kItemsPerThread;  // 2048 keys per CTA per pass
+
+// fp32 -> uint32 whose unsigned order is the float order; -0 -> +0 first; NaN (any sign) -> largest.
+__device__ __forceinline__ uint32_t orderable(float v) {
+  if (v != v) return 0xFFFFFFFFu;
+  v += 0.0f;  // -0 -> +0
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) make_keys_kernel(const float* __restrict__ f, int64_t N, int descending,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const uint32_t k = orderable(f[i]);
+    keys[i] = descending ? ~k : k;  // descending + stable == ascending on the complemented key
+    idx[i] = (uint32_t)i;
+  }
+}
+
+// counts[d * n_tiles + tile]
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t N, int shift,
+                                                                  uint32_t* __restrict__ counts, int n_tiles) {
+  __shared__ uint32_t h[kRadix];
+  for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+#pragma unroll
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const int64_t i = base + it * kSortThreads + threadIdx.x;
+    if (i < N) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts[(int64_t)d * n_tiles + blockIdx.x] = h[d];
+}
+
+// per digit d (one CTA each): exclusive scan in place of counts[d][0..n_tiles) and the digit total.
+__global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ counts, int n_tiles, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t warp_tot[8];
+  __shared__ uint32_t carry_s, chunk_s;
+  uint32_t* row = counts + (int64_t)blockIdx.x * n_tiles;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 256) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < n_tiles ? row[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t t = lane < 8 ? warp_tot[lane] : 0u;
+      uint32_t ti = t;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      if (lane < 8) warp_tot[lane] = ti - t;  // exclusive warp offsets
+      if (lane == 7) chunk_s = ti;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    if (i < n_tiles) row[i] = carry + warp_tot[wid] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + chunk_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+}
+
+// stable scatter of one tile.  Item order inside a tile: warp w owns the contiguous range
+// [w*256, (w+1)*256); iteration `it` covers 32 consecutive items, lane = position.
+__global__ void __launch_bounds__(kSortThreads)
+    radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ keys_out,
+                         uint32_t* __restrict__ idx_out, int64_t N, int shift, const uint32_t* __restrict__ offsets, int n_tiles,
+                         const uint32_t* __restrict__ totals) {
+  __shared__ uint32_t wcount[kSortWarps][kRadix];  // per-warp digit counts, then per-warp exclusive bases
+  __shared__ uint32_t digit_base[kRadix];          // exclusive scan of the digit totals
+  __shared__ uint32_t wtot[kSortWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&wcount[0][0])[i] = 0;
+  {  // kSortThreads == kRadix: thread d owns digit d
+    const uint32_t t = totals[threadIdx.x];
+    uint32_t incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) wb += w < wid ? wtot[w] : 0u;
+    digit_base[threadIdx.x] = wb + incl - t;
+  }
+  __syncthreads();
+
+  const int64_t wbase = (int64_t)blockIdx.x * kTile + (int64_t)wid * (32 * kItemsPerThread);
+  uint32_t key[kItemsPerThread], val[kItemsPerThread], rnk[kItemsPerThread];
+#pragma unroll
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const int64_t i = wbase + it * 32 + lane;
+    const bool ok = i < N;
+    key[it] = ok ? keys_in[i] : 0xFFFFFFFFu;
+    val[it] = ok ? idx_in[i] : 0u;
+    const uint32_t d = (key[it] >> shift) & (kRadix - 1);
+    // lanes holding the same digit (invalid lanes form their own group via the extra bit)
+    const uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (kRadix + 1u));
+    const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (ok && below == 0) {  // group leader: lowest lane of the group
+      base = wcount[wid][d];
+      wcount[wid][d] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+    rnk[it] = base + below;
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over the warps (in warp order) + global tile offset
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
+    uint32_t run = digit_base[d] + offsets[(int64_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = wcount[w][d];
+      wcount[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const int64_t i = wbase + it * 32 + lane;
+    if (i < N) {
+      const uint32_t d = (key[it] >> shift) & (kRadix - 1);
+      const uint32_t pos = wcount[wid][d] + rnk[it];
+      keys_out[pos] = key[it];
+      idx_out[pos] = val[it];
+    }
+  }
+}
+
+// ---- utility tables -------------------------------------------------------------------------------
+// sum over p of max(0, ln(N/2+1) - ln(N-p)) (fp32 terms, double accumulation); single CTA.
+__global__ void __launch_bounds__(1024) nes_table_sum_kernel(int64_t N, float* __restrict__ out_sum) {
+  __shared__ double sm[33];
+  const float Nf = (float)N;
+  const float top = logf(Nf / 2.0f + 1.0f);
+  double acc = 0.0;
+  for (int64_t p = threadIdx.x; p < N; p += 1024) acc += (double)fmaxf(0.0f, top - logf(Nf - (float)p));
+  const double tot = block_sum<double>(acc, sm);
+  if (threadIdx.x == 0) *out_sum = (float)tot;
+}
+
+// position p in sorted order (worst first) -> utility, scattered to the solution's slot
+__global__ void __launch_bounds__(256) scatter_utilities_kernel(const uint32_t* __restrict__ idx, int64_t N, int method,
+                                                                const float* __restrict__ nes_sum, float* __restrict__ w,
+                                                                int64_t* __restrict__ perm) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const uint32_t i = idx[p];
+  float u;
+  if (method == EVOK_RANK_CENTERED) {
+    u = __fdiv_rn((float)p, (float)(N - 1)) - 0.5f;
+  } else if (method == EVOK_RANK_LINEAR) {
+    u = __fdiv_rn((float)p, (float)(N - 1));
+  } else {  // NES
+    const float Nf = (float)N;
+    const float t = fmaxf(0.0f, logf(Nf / 2.0f + 1.0f) - logf(Nf - (float)p));
+    u = __fdiv_rn(t, *nes_sum) - __fdiv_rn(1.0f, Nf);
+  }
+  w[i] = u;
+  if (perm) perm[p] = (int64_t)i;
+}
+
+__global__ void __launch_bounds__(256) write_perm_kernel(const uint32_t* __restrict__ idx, int64_t N, int64_t* __restrict__ perm) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < N) perm[p] = (int64_t)idx[p];
+}
+
+// normalized / raw: no sort.  stats[0] = mean, stats[1] = unbiased std of g = +-f (double accumulation).
+__global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict__ f, int64_t N, float sign, float* __restrict__ stats) {
+  __shared__ double sm[33];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 1024) s += (double)(sign * f[i]);
+  const double mean = block_sum<double>(s, sm) / (double)N;
+  double q = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 1024) {
+    const double d = (double)(sign * f[i]) - mean;
+    q += d * d;
+  }
+  const double var = block_sum<double>(q, sm) / (double)(N - 1);
+  if (threadIdx.x == 0) {
+    stats[0] = (float)mean;
+    stats[1] = (float)sqrt(var);
+  }
+}
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ f, int64_t N, float sign, const float* __restrict__ stats,
+                                                     int normalized, float* __restrict__ w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float g = sign * f[i];
+  w[i] = normalized ? __fdiv_rn(g - stats[0], stats[1]) : g;
+}
+
+// in-place weight adjustments
+__global__ void __launch_bounds__(1024) weights_adjust_kernel(float* __restrict__ w, int64_t N, int mode) {
+  __shared__ double sm[33];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 1024) s += mode == 1 ? (double)w[i] : (double)fabsf(w[i]);
+  const double tot = block_sum<double>(s, sm);
+  if (mode == 1) {
+    const float mean = (float)(tot / (double)N);
+    for (int64_t i = threadIdx.x; i < N; i += 1024) w[i] -= mean;
+  } else {
+    const float d = (float)tot;
+    for (int64_t i = threadIdx.x; i < N; i += 1024) w[i] = __fdiv_rn(w[i], d);
+  }
+}
+
+__global__ void __launch_bounds__(256) elite_mask_kernel(const uint32_t* __restrict__ idx, int64_t N, int64_t num_elites,
+                                                         float* __restrict__ mask) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < N) mask[idx[p]] = p < num_elites ? 1.0f : 0.0f;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct SortPlan {
+  int64_t N;
+  int n_tiles;
+  size_t off_keys0, off_keys1, off_idx0, off_idx1, off_counts, off_totals, off_scalar, total;
+};
+
+static SortPlan make_plan(int64_t N) {
+  SortPlan p;
+  p.N = N;
+  p.n_tiles = (int)((N + kTile - 1) / kTile);
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o = 0;
+  p.off_keys0 = o; o += al((size_t)N * 4);
+  p.off_keys1 = o; o += al((size_t)N * 4);
+  p.off_idx0 = o; o += al((size_t)N * 4);
+  p.off_idx1 = o; o += al((size_t)N * 4);
+  p.off_counts = o; o += al((size_t)kRadix * p.n_tiles * 4);
+  p.off_totals = o; o += al((size_t)kRadix * 4);
+  p.off_scalar = o; o += 256;
+  p.total = o;
+  return p;
+}
+
+// sorts; returns the device pointer (inside ws) of the sorted index array
+static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const SortPlan& p, cudaStream_t st, uint32_t** sorted_idx) {
+  char* base = (char*)ws;
+  uint32_t* keys[2] = {(uint32_t*)(base + p.off_keys0), (uint32_t*)(base + p.off_keys1)};
+  uint32_t* idx[2] = {(uint32_t*)(base + p.off_idx0), (uint32_t*)(base + p.off_idx1)};
+  uint32_t* counts = (uint32_t*)(base + p.off_counts);
+  uint32_t* totals = (uint32_t*)(base + p.off_totals);
+  make_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f, N, descending, keys[0], idx[0]);
+  EVOK_CHECK_LAUNCH();
+  int cur = 0;
+  for (int pass = 0; pass < 32 / kRadixBits; ++pass) {
+    const int shift = pass * kRadixBits;
+    radix_hist_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], N, shift, counts, p.n_tiles);
+    digit_scan_kernel<<<kRadix, 256, 0, st>>>(counts, p.n_tiles, totals);
+    radix_scatter_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
+    EVOK_CHECK_LAUNCH();
+    cur ^= 1;
+  }
+  *sorted_idx = idx[cur];
+  return 0;
+}
+
+}  // namespace evok
+
+using namespace evok;
+
+extern "C" EVOK_API size_t evok_rank_workspace_bytes(int64_t N) {
+  if (N <= 0) return 256;
+  return make_plan(N).total;
+}
+
+extern "C" EVOK_API int evok_rank(int method, const float* f, int64_t N, int higher_is_better, float* w, int64_t* perm, void* ws,
+                         size_t ws_bytes, void* stream) {
+  if (!f || !w || !ws) return EVOK_E_NULLPTR;
+  if (method < EVOK_RANK_CENTERED || method > EVOK_RANK_RAW) return EVOK_E_BADENUM;
+  if (N < 0 || N >= (int64_t)1 << 32) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  const SortPlan p = make_plan(N);
+  if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* scalar = (float*)((char*)ws + p.off_scalar);
+  const unsigned nb = (unsigned)((N + 255) / 256);
+  if (method == EVOK_RANK_NORMALIZED || method == EVOK_RANK_RAW) {
+    const float sign = higher_is_better ? 1.0f : -1.0f;
+    if (method == EVOK_RANK_NORMALIZED) mean_std_kernel<<<1, 1024, 0, st>>>(f, N, sign, scalar);
+    affine_kernel<<<nb, 256, 0, st>>>(f, N, sign, scalar, method == EVOK_RANK_NORMALIZED, w);
+    EVOK_CHECK_LAUNCH();
+    if (perm) {
+      uint32_t* sidx = nullptr;
+      int rc = sort_pairs(f, N, !higher_is_better, ws, p, st, &sidx);
+      if (rc) return rc;
+      write_perm_kernel<<<nb, 256, 0, st>>>(sidx, N, perm);
+      EVOK_CHECK_LAUNCH();
+    }
+    return 0;
+  }
+  uint32_t* sidx = nullptr;
+  int rc = sort_pairs(f, N, !higher_is_better, ws, p, st, &sidx);
+  if (rc) return rc;
+  if (method == EVOK_RANK_NES) nes_table_sum_kernel<<<1, 1024, 0, st>>>(N, scalar);
+  scatter_utilities_kernel<<<nb, 256, 0, st>>>(sidx, N, method, scalar, w, perm);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_argsort(const float* keys, int64_t N, int descending, int64_t* perm, void* ws, size_t ws_bytes, void* stream) {
+  if (!keys || !perm || !ws) return EVOK_E_NULLPTR;
+  if (N < 0 || N >= (int64_t)1 << 32) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  const SortPlan p = make_plan(N);
+  if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* sidx = nullptr;
+  int rc = sort_pairs(keys, N, descending, ws, p, st, &sidx);
+  if (rc) return rc;
+  write_perm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sidx, N, perm);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_weights_adjust(float* w, int64_t N, int mode, void* stream) {
+  if (!w) return EVOK_E_NULLPTR;
+  if (mode != 1 && mode != 2) return EVOK_E_BADENUM;
+  if (N < 0) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  weights_adjust_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w, N, mode);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_elite_mask(const float* w, int64_t N, int64_t num_elites, float* mask, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !mask || !ws) return EVOK_E_NULLPTR;
+  if (N < 0 || N >= (int64_t)1 << 32 || num_elites < 0 || num_elites > N) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  const SortPlan p = make_plan(N);
+  if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* sidx = nullptr;
+  int rc = sort_pairs(w, N, /*descending=*/1, ws, p, st, &sidx);
+  if (rc) return rc;
+  elite_mask_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sidx, N, num_elites, mask);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,206 @@
+// K1 / K2: fused Philox sampling -> perturbation write -> objective row-reduction, and the stand-alone
+// evaluation kernel.  HBM-bound design: one warp owns one direction (a +/- row pair) or one row; every
+// lane produces 4 consecutive columns per step from ONE Philox4x32-10 call, writes them with 128-bit
+// streaming stores (512 contiguous bytes per warp-row) and folds them into the objective accumulators
+// while they are still in registers, so the population is written once and never re-read for evaluation.
+#include "evok_common.cuh"
+
+namespace evok {
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+constexpr int kSampleThreads = 256;
+
+template <int OBJ, bool SYM, bool STORE, bool VEC>
+__global__ void __launch_bounds__(kSampleThreads)
+    sample_eval_kernel(float* __restrict__ X, int64_t ldx, const float* __restrict__ mu, const float* __restrict__ sigma,
+                       int64_t row0, int64_t n_units, int64_t D, uint64_t seed, uint64_t stream_id, float* __restrict__ f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (kSampleThreads / 32);
+  const int64_t gw = (int64_t)blockIdx.x * (kSampleThreads / 32) + (threadIdx.x >> 5);
+  const uint32_t nq = (uint32_t)((D + 3) >> 2);
+  const uint64_t unit0 = (uint64_t)(SYM ? (row0 >> 1) : row0);
+
+  for (int64_t u = gw; u < n_units; u += warps_total) {
+    ObjAcc<OBJ> accp, accm;
+    const int64_t r = SYM ? 2 * u : u;
+    float* xp = STORE ? X + r * ldx : nullptr;
+    float* xm = STORE ? xp + ldx : nullptr;
+    for (uint32_t q = lane; q < nq; q += 32) {
+      float z[4];
+      normals4(seed, stream_id, unit0 + (uint64_t)u, q, z);
+      const int64_t j = (int64_t)q << 2;
+      if (VEC) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mu + j));
+        const float4 s = __ldg(reinterpret_cast<const float4*>(sigma + j));
+        const float p0 = fmaf(s.x, z[0], m.x), p1 = fmaf(s.y, z[1], m.y), p2 = fmaf(s.z, z[2], m.z), p3 = fmaf(s.w, z[3], m.w);
+        if (STORE) st_stream4(xp + j, p0, p1, p2, p3);
+        accp.add(p0); accp.add(p1); accp.add(p2); accp.add(p3);
+        if (SYM) {
+          const float n0 = fmaf(-s.x, z[0], m.x), n1 = fmaf(-s.y, z[1], m.y), n2 = fmaf(-s.z, z[2], m.z), n3 = fmaf(-s.w, z[3], m.w);
+          if (STORE) st_stream4(xm + j, n0, n1, n2, n3);
+          accm.add(n0); accm.add(n1); accm.add(n2); accm.add(n3);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (j + c < D) {
+            const float m = __ldg(mu + j + c), s = __ldg(sigma + j + c);
+            const float p = fmaf(s, z[c], m);
+            if (STORE) st_stream1(xp + j + c, p);
+            accp.add(p);
+            if (SYM) {
+              const float n = fmaf(-s, z[c], m);
+              if (STORE) st_stream1(xm + j + c, n);
+              accm.add(n);
+            }
+          }
+        }
+      }
+    }
+    if (OBJ != EVOK_OBJ_NONE) {
+      const float fp = accp.finish(D);
+      float fm = 0.f;
+      if (SYM) fm = accm.finish(D);
+      if (lane == 0) {
+        f[r] = fp;
+        if (SYM) f[r + 1] = fm;
+      }
+    }
+  }
+}
+
+constexpr int kEvalThreads = 256;
+
+template <int OBJ, bool VEC>
+__global__ void __launch_bounds__(kEvalThreads)
+    eval_kernel(const float* __restrict__ X, int64_t ldx, int64_t n_rows, int64_t D, float* __restrict__ f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (kEvalThreads / 32);
+  const int64_t gw = (int64_t)blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5);
+  for (int64_t r = gw; r < n_rows; r += warps_total) {
+    ObjAcc<OBJ> acc;
+    const float* x = X + r * ldx;
+    if (VEC) {
+      const int64_t nq = D >> 2;
+      int64_t q = lane;
+      // 4 independent 128-bit loads in flight per lane
+      for (; q + 96 < nq; q += 128) {
+        const float4 a = ld_stream4(x + 4 * q), b = ld_stream4(x + 4 * (q + 32)), c = ld_stream4(x + 4 * (q + 64)),
+                     d = ld_stream4(x + 4 * (q + 96));
+        acc.add(a.x); acc.add(a.y); acc.add(a.z); acc.add(a.w);
+        acc.add(b.x); acc.add(b.y); acc.add(b.z); acc.add(b.w);
+        acc.add(c.x); acc.add(c.y); acc.add(c.z); acc.add(c.w);
+        acc.add(d.x); acc.add(d.y); acc.add(d.z); acc.add(d.w);
+      }
+      for (; q < nq; q += 32) {
+        const float4 a = ld_stream4(x + 4 * q);
+        acc.add(a.x); acc.add(a.y); acc.add(a.z); acc.add(a.w);
+      }
+    } else {
+      for (int64_t j = lane; j < D; j += 32) acc.add(ld_stream1(x + j));
+    }
+    const float v = acc.finish(D);
+    if (lane == 0) f[r] = v;
+  }
+}
+
+template <typename K>
+static int resident_grid(K kernel, int threads, int64_t units_per_cta_needed) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+  int64_t g = (int64_t)per_sm * sm_count();
+  if (g > units_per_cta_needed) g = units_per_cta_needed;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int OBJ, bool SYM, bool STORE>
+static int launch_sample(float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
+                         uint64_t seed, uint64_t stream_id, float* f, cudaStream_t st) {
+  const int64_t n_units = SYM ? n_rows / 2 : n_rows;
+  const bool vec = (D % 4 == 0) && aligned16(mu) && aligned16(sigma) && (!STORE || (aligned16(X) && ldx % 4 == 0));
+  const int64_t ctas_needed = (n_units + (kSampleThreads / 32) - 1) / (kSampleThreads / 32);
+  if (vec) {
+    auto k = sample_eval_kernel<OBJ, SYM, STORE, true>;
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, seed, stream_id, f);
+  } else {
+    auto k = sample_eval_kernel<OBJ, SYM, STORE, false>;
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, seed, stream_id, f);
+  }
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int OBJ>
+static int dispatch_sample(float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
+                           int symmetric, uint64_t seed, uint64_t stream_id, float* f, cudaStream_t st) {
+  if (symmetric) {
+    return X ? launch_sample<OBJ, true, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st)
+             : launch_sample<OBJ, true, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st);
+  }
+  return X ? launch_sample<OBJ, false, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st)
+           : launch_sample<OBJ, false, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st);
+}
+
+template <int OBJ>
+static int launch_eval(const float* X, int64_t ldx, int64_t n_rows, int64_t D, float* f, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && aligned16(X) && (ldx % 4 == 0);
+  const int64_t ctas_needed = (n_rows + (kEvalThreads / 32) - 1) / (kEvalThreads / 32);
+  if (vec) {
+    auto k = eval_kernel<OBJ, true>;
+    k<<<resident_grid(k, kEvalThreads, ctas_needed), kEvalThreads, 0, st>>>(X, ldx, n_rows, D, f);
+  } else {
+    auto k = eval_kernel<OBJ, false>;
+    k<<<resident_grid(k, kEvalThreads, ctas_needed), kEvalThreads, 0, st>>>(X, ldx, n_rows, D, f);
+  }
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace evok
+
+using namespace evok;
+
+extern "C" EVOK_API int evok_sample_eval(int objective, float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0,
+                                int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, float* f,
+                                void* stream) {
+  if (!mu || !sigma) return EVOK_E_NULLPTR;
+  if (objective < 0 || objective >= EVOK_OBJ_COUNT) return EVOK_E_BADENUM;
+  if (objective == EVOK_OBJ_NONE && !X) return EVOK_E_NULLPTR;
+  if (objective != EVOK_OBJ_NONE && !f) return EVOK_E_NULLPTR;
+  if (n_rows < 0 || D <= 0 || row0 < 0 || (X && ldx < D)) return EVOK_E_BADSIZE;
+  if (symmetric && ((n_rows & 1) || (row0 & 1))) return EVOK_E_ODDROWS;
+  if (n_rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (objective) {
+    case EVOK_OBJ_NONE: return dispatch_sample<EVOK_OBJ_NONE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
+    case EVOK_OBJ_SPHERE: return dispatch_sample<EVOK_OBJ_SPHERE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
+    case EVOK_OBJ_RASTRIGIN: return dispatch_sample<EVOK_OBJ_RASTRIGIN>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
+    case EVOK_OBJ_ACKLEY: return dispatch_sample<EVOK_OBJ_ACKLEY>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
+  }
+  return EVOK_E_BADENUM;
+}
+
+extern "C" EVOK_API int evok_eval(int objective, const float* X, int64_t ldx, int64_t n_rows, int64_t D, float* f, void* stream) {
+  if (!X || !f) return EVOK_E_NULLPTR;
+  if (objective <= EVOK_OBJ_NONE || objective >= EVOK_OBJ_COUNT) return EVOK_E_BADENUM;
+  if (n_rows < 0 || D <= 0 || ldx < D) return EVOK_E_BADSIZE;
+  if (n_rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (objective) {
+    case EVOK_OBJ_SPHERE: return launch_eval<EVOK_OBJ_SPHERE>(X, ldx, n_rows, D, f, st);
+    case EVOK_OBJ_RASTRIGIN: return launch_eval<EVOK_OBJ_RASTRIGIN>(X, ldx, n_rows, D, f, st);
+    case EVOK_OBJ_ACKLEY: return launch_eval<EVOK_OBJ_ACKLEY>(X, ldx, n_rows, D, f, st);
+  }
+  return EVOK_E_BADENUM;
+}

@@ -1,0 +1,121 @@
+"""Population sharding over the GPUs of one box with torch.distributed (NCCL over NVLink; gloo in the CPU tests).
+
+This replaces the reference's Ray-actor path (`Problem.sample_and_compute_gradients`, core.py:2762-3073 and
+`GaussianSearchAlgorithm._step_distributed`, algorithms/distributed/gaussian.py:199-272).  One process per GPU
+(launched with torchrun).  Per generation each rank
+
+  1. samples and evaluates its own contiguous row shard (K1+K2).  The Philox counter of a draw is a function of the
+     GLOBAL row index, so the population is identical for every world size;
+  2. all-gathers the local fitness slice -> the full fitness vector (N floats: 4 MB at N = 1 M);
+  3. ranks the full vector (K3, replicated) and keeps its slice of the utilities;
+  4. reduces its partial gradients over its rows (K4) and all-reduces the stacked (mu, sigma) partials (2*D floats);
+  5. applies the (replicated) update (K5).
+
+Unlike the reference (which ranks *locally* per actor and averages the per-actor gradients), ranking is global, so an
+R-GPU run reproduces the single-GPU run at the same population size up to fp32 summation order.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .tools.misc import split_workload
+from .tools.ranking import rank
+
+
+def world() -> tuple:
+    """(rank, world_size) of the default process group; (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_rows(popsize: int, world_size: int, rank_: int, symmetric: bool) -> tuple:
+    """Contiguous row range [row0, row0 + n) of this rank; antithetic pairs are never split."""
+    unit = 2 if symmetric else 1
+    if popsize % unit != 0:
+        raise ValueError(f"popsize ({popsize}) must be even for a symmetric distribution")
+    shares = split_workload(popsize // unit, world_size)
+    row0 = unit * sum(shares[:rank_])
+    return row0, unit * shares[rank_], [unit * s for s in shares]
+
+
+def all_gather_rows(local: torch.Tensor, counts: list) -> torch.Tensor:
+    """Concatenate the 1-D `local` tensors of all ranks (possibly of different lengths `counts`) in rank order."""
+    rank_, ws = world()
+    if ws == 1:
+        return local
+    if len(set(counts)) == 1:
+        out = torch.empty(sum(counts), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    width = max(counts)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    gathered = torch.empty(ws * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, padded)
+    return torch.cat([gathered[r * width: r * width + counts[r]] for r in range(ws)])
+
+
+def broadcast_seed(problem) -> None:
+    """Make every rank draw from the same Philox key (rank 0's) -- required for the population to be rank-count invariant."""
+    rank_, ws = world()
+    if ws == 1 or getattr(problem, "_seed_synced", False):
+        return
+    t = torch.tensor([problem._philox_seed & 0x7FFFFFFFFFFFFFFF, problem._philox_stream], dtype=torch.int64, device=problem.device)
+    dist.broadcast(t, src=0)
+    problem._philox_seed, problem._philox_stream = int(t[0].item()), int(t[1].item())
+    problem._seed_synced = True
+
+
+def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_index: int, ranking_method: Optional[str]) -> dict:
+    """One sample -> evaluate -> (global) rank -> gradient pass over this rank's row shard; see the module docstring.
+    Returns {"gradients", "num_solutions", "mean_eval"} like the reference's `_sample_and_compute_gradients`
+    (core.py:3156-3301), with gradients on `distribution.device`."""
+    from .core import SolutionBatch
+
+    rank_, ws = world()
+    home_device = distribution.device
+    dev_dist = distribution.to(problem.device)
+    symmetric = bool(getattr(dev_dist, "SYMMETRIC", False))
+    if ws > 1 and not hasattr(dev_dist, "partial_gradients"):
+        raise NotImplementedError(f"{type(dev_dist).__name__} cannot be sharded over ranks (full-covariance search is a small-D method)")
+    row0, n_local, counts = shard_rows(popsize, ws, rank_, symmetric)
+    broadcast_seed(problem)
+
+    cache = problem.__dict__.setdefault("_grad_batches", {})
+    batch = cache.get(n_local)
+    if batch is None:
+        batch = cache[n_local] = SolutionBatch(problem, n_local, device=problem.device, empty=True)
+    problem.philox_row0 = row0
+    try:
+        problem.sample_and_evaluate(dev_dist, batch)
+    finally:
+        problem.philox_row0 = 0
+
+    samples = batch.access_values(keep_evals=True)
+    f_local = batch.access_evals(obj_index)
+    f_all = all_gather_rows(f_local.to(dev_dist.dtype), counts)
+    sense = problem.senses[obj_index]
+    method = "raw" if ranking_method is None else ranking_method
+    weights_all = rank(f_all, method, higher_is_better=(sense == "max"))
+
+    if hasattr(dev_dist, "partial_gradients"):
+        partial = dev_dist.partial_gradients(samples, weights_all, row0, method)
+        if ws > 1:
+            keys = sorted(partial)
+            stacked = torch.stack([partial[k] for k in keys])
+            dist.all_reduce(stacked, op=dist.ReduceOp.SUM)
+            partial = {k: stacked[i] for i, k in enumerate(keys)}
+        grads = dev_dist.finalize_gradients(partial, popsize)
+    else:
+        grads = dev_dist._compute_gradients(samples, weights_all, method)
+
+    mean_eval = torch.mean(f_all)  # 0-dim tensor: converting it to float is the caller's (lazy) choice, no forced sync here
+    if home_device != problem.device:
+        grads = {k: v.to(home_device) for k, v in grads.items()}
+        mean_eval = mean_eval.to(home_device)
+    return {"gradients": grads, "num_solutions": popsize, "mean_eval": mean_eval}

@@ -1,0 +1,208 @@
+"""Tensor-level entry points of the sm_100a kernels (CUDA, fp32 only).
+
+Each function validates its tensors, pulls raw pointers + the current stream and calls the C ABI of
+libevok.so (include/evok.h).  Callers in this package decide *whether* a tensor goes to these kernels
+(`uses_kernels`); there is no silent fallback from here: a missing library raises.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+
+OBJ_NONE, OBJ_SPHERE, OBJ_RASTRIGIN, OBJ_ACKLEY = 0, 1, 2, 3
+OBJECTIVE_IDS = {"sphere": OBJ_SPHERE, "rastrigin": OBJ_RASTRIGIN, "ackley": OBJ_ACKLEY}
+RANK_IDS = {"centered": 0, "linear": 1, "nes": 2, "normalized": 3, "raw": 4}
+GRAD_SEPARABLE, GRAD_SYMMETRIC, GRAD_EXP, GRAD_MOMENTS = 0, 1, 2, 3
+NAN = float("nan")
+
+
+def uses_kernels(t: torch.Tensor) -> bool:
+    """True for the tensors the hand-written kernels handle: CUDA + float32."""
+    return t.is_cuda and t.dtype == torch.float32
+
+
+def _vec(t: torch.Tensor, name: str, n: Optional[int] = None) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.ndim == 1 and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous 1-D float32 CUDA tensor, got {tuple(t.shape)} {t.dtype} {t.device}")
+    if n is not None and t.numel() != n:
+        raise ValueError(f"{name}: expected length {n}, got {t.numel()}")
+    return t
+
+
+def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.ndim == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]):
+        raise ValueError(f"{name}: expected a row-major 2-D float32 CUDA tensor, got {tuple(t.shape)} strides {t.stride()} {t.dtype}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ K1 / K2
+def sample_eval(objective: int, X: Optional[torch.Tensor], mu: torch.Tensor, sigma: torch.Tensor, *, n_rows: int, symmetric: bool,
+                seed: int, stream_id: int, row0: int = 0, f: Optional[torch.Tensor] = None) -> None:
+    D = mu.numel()
+    _vec(mu, "mu"); _vec(sigma, "sigma", D)
+    ldx = 0
+    if X is not None:
+        _mat(X, "X")
+        if X.shape != (n_rows, D):
+            raise ValueError(f"X: expected shape {(n_rows, D)}, got {tuple(X.shape)}")
+        ldx = X.stride(0)
+    if f is not None:
+        _vec(f, "f", n_rows)
+    rc = nat.lib().evok_sample_eval(objective, nat.ptr(X), ldx, mu.data_ptr(), sigma.data_ptr(), row0, n_rows, D, int(symmetric),
+                                    seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, nat.ptr(f), nat.stream_of(mu))
+    nat.check(rc, "evok_sample_eval")
+
+
+def evaluate(objective: int, X: torch.Tensor, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _mat(X, "X")
+    n, D = X.shape
+    if f is None:
+        f = torch.empty(n, dtype=torch.float32, device=X.device)
+    _vec(f, "f", n)
+    nat.check(nat.lib().evok_eval(objective, X.data_ptr(), X.stride(0), n, D, f.data_ptr(), nat.stream_of(X)), "evok_eval")
+    return f
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def _rank_ws(device: torch.device, n: int) -> torch.Tensor:
+    return nat.workspace(device, nat.lib().evok_rank_workspace_bytes(n), "rank")
+
+
+def rank(f: torch.Tensor, method: str, higher_is_better: bool, out: Optional[torch.Tensor] = None,
+         perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    f = _vec(f, "fitnesses")
+    n = f.numel()
+    w = torch.empty_like(f) if out is None else _vec(out, "out", n)
+    if perm is not None and not (perm.is_cuda and perm.dtype == torch.int64 and perm.is_contiguous() and perm.numel() == n):
+        raise ValueError("perm: expected a contiguous int64 CUDA tensor of the same length")
+    ws = _rank_ws(f.device, n)
+    rc = nat.lib().evok_rank(RANK_IDS[method], f.data_ptr(), n, int(bool(higher_is_better)), w.data_ptr(), nat.ptr(perm), ws.data_ptr(),
+                             ws.numel(), nat.stream_of(f))
+    nat.check(rc, "evok_rank")
+    return w
+
+
+def argsort(keys: torch.Tensor, descending: bool) -> torch.Tensor:
+    keys = _vec(keys, "keys")
+    n = keys.numel()
+    perm = torch.empty(n, dtype=torch.int64, device=keys.device)
+    ws = _rank_ws(keys.device, n)
+    nat.check(nat.lib().evok_argsort(keys.data_ptr(), n, int(bool(descending)), perm.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     nat.stream_of(keys)), "evok_argsort")
+    return perm
+
+
+def weights_adjust_(w: torch.Tensor, mode: int) -> torch.Tensor:
+    _vec(w, "weights")
+    nat.check(nat.lib().evok_weights_adjust(w.data_ptr(), w.numel(), mode, nat.stream_of(w)), "evok_weights_adjust")
+    return w
+
+
+def elite_mask(w: torch.Tensor, num_elites: int) -> torch.Tensor:
+    _vec(w, "weights")
+    n = w.numel()
+    mask = torch.empty_like(w)
+    ws = _rank_ws(w.device, n)
+    nat.check(nat.lib().evok_elite_mask(w.data_ptr(), n, num_elites, mask.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(w)),
+              "evok_elite_mask")
+    return mask
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def grad(form: int, X: torch.Tensor, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, scale_mu: float, scale_sigma: float,
+         out_mu: Optional[torch.Tensor] = None, out_sigma: Optional[torch.Tensor] = None) -> tuple:
+    _mat(X, "samples")
+    n, D = X.shape
+    _vec(w, "weights", n); _vec(mu, "mu", D); _vec(sigma, "sigma", D)
+    out_mu = torch.empty_like(mu) if out_mu is None else _vec(out_mu, "out_mu", D)
+    out_sigma = torch.empty_like(mu) if out_sigma is None else _vec(out_sigma, "out_sigma", D)
+    ws = nat.workspace(X.device, nat.lib().evok_grad_workspace_bytes(n, D), "grad")
+    rc = nat.lib().evok_grad(form, X.data_ptr(), X.stride(0), w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), n, D, scale_mu, scale_sigma,
+                             out_mu.data_ptr(), out_sigma.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(X))
+    nat.check(rc, "evok_grad")
+    return out_mu, out_sigma
+
+
+def grad_regen(form: int, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, *, seed: int, stream_id: int, row0: int,
+               scale_mu: float, scale_sigma: float, out_mu: Optional[torch.Tensor] = None,
+               out_sigma: Optional[torch.Tensor] = None) -> tuple:
+    n, D = w.numel(), mu.numel()
+    _vec(w, "weights"); _vec(mu, "mu"); _vec(sigma, "sigma", D)
+    out_mu = torch.empty_like(mu) if out_mu is None else _vec(out_mu, "out_mu", D)
+    out_sigma = torch.empty_like(mu) if out_sigma is None else _vec(out_sigma, "out_sigma", D)
+    ws = nat.workspace(mu.device, nat.lib().evok_grad_workspace_bytes(n, D), "grad")
+    rc = nat.lib().evok_grad_regen(form, w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), row0, n, D, seed & 0xFFFFFFFFFFFFFFFF,
+                                   stream_id & 0xFFFFFFFFFFFFFFFF, scale_mu, scale_sigma, out_mu.data_ptr(), out_sigma.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), nat.stream_of(mu))
+    nat.check(rc, "evok_grad_regen")
+    return out_mu, out_sigma
+
+
+# ------------------------------------------------------------------------------------------------ K5
+def clipup_step(g: torch.Tensor, velocity: torch.Tensor, stepsize: float, momentum: float, max_speed: float,
+                step_out: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None) -> None:
+    D = g.numel()
+    _vec(g, "g"); _vec(velocity, "velocity", D)
+    rc = nat.lib().evok_clipup_step(g.data_ptr(), D, velocity.data_ptr(), stepsize, momentum, max_speed, nat.ptr(step_out), nat.ptr(mu),
+                                    nat.stream_of(g))
+    nat.check(rc, "evok_clipup_step")
+
+
+def adam_step(g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, t: int, lr: float, beta1: float, beta2: float, eps: float,
+              step_out: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None) -> None:
+    D = g.numel()
+    _vec(g, "g"); _vec(m, "m", D); _vec(v, "v", D)
+    rc = nat.lib().evok_adam_step(g.data_ptr(), D, m.data_ptr(), v.data_ptr(), t, lr, beta1, beta2, eps, nat.ptr(step_out), nat.ptr(mu),
+                                  nat.stream_of(g))
+    nat.check(rc, "evok_adam_step")
+
+
+def sgd_step(g: torch.Tensor, buf: Optional[torch.Tensor], first_step: bool, lr: float, momentum: float,
+             step_out: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None) -> None:
+    D = g.numel()
+    _vec(g, "g")
+    rc = nat.lib().evok_sgd_step(g.data_ptr(), D, nat.ptr(buf), int(first_step), lr, momentum, nat.ptr(step_out), nat.ptr(mu),
+                                 nat.stream_of(g))
+    nat.check(rc, "evok_sgd_step")
+
+
+def axpy_(mu: torch.Tensor, g: torch.Tensor, lr: float) -> None:
+    D = g.numel()
+    _vec(g, "g"); _vec(mu, "mu", D)
+    nat.check(nat.lib().evok_axpy(g.data_ptr(), D, lr, mu.data_ptr(), nat.stream_of(g)), "evok_axpy")
+
+
+def _bound(x, D: int, device) -> tuple:
+    """(vector pointer or None, scalar) for a None / scalar / vector bound."""
+    if x is None:
+        return None, NAN
+    if isinstance(x, torch.Tensor) and x.ndim >= 1 and x.numel() > 1:
+        v = x.to(device=device, dtype=torch.float32).contiguous()
+        if v.numel() != D:
+            raise IndexError(f"bound vector has length {v.numel()}, expected {D}")
+        return v, NAN
+    return None, float(x)
+
+
+def sigma_update_(sigma: torch.Tensor, g: torch.Tensor, lr: float, exp_form: bool, lb=None, ub=None, max_change=None) -> None:
+    D = sigma.numel()
+    _vec(sigma, "sigma"); _vec(g, "g", D)
+    lbv, lbs = _bound(lb, D, sigma.device)
+    ubv, ubs = _bound(ub, D, sigma.device)
+    mcv, mcs = _bound(max_change, D, sigma.device)
+    rc = nat.lib().evok_sigma_update(sigma.data_ptr(), g.data_ptr(), D, lr, int(exp_form), nat.ptr(lbv), lbs, nat.ptr(ubv), ubs,
+                                     nat.ptr(mcv), mcs, nat.stream_of(sigma))
+    nat.check(rc, "evok_sigma_update")
+
+
+def cem_finalize(s1: torch.Tensor, s2: torch.Tensor, sigma: torch.Tensor, num_elites: int) -> tuple:
+    D = sigma.numel()
+    gm, gs = torch.empty_like(sigma), torch.empty_like(sigma)
+    nat.check(nat.lib().evok_cem_finalize(s1.data_ptr(), s2.data_ptr(), sigma.data_ptr(), D, num_elites, gm.data_ptr(), gs.data_ptr(),
+                                          nat.stream_of(sigma)), "evok_cem_finalize")
+    return gm, gs

@@ -1,0 +1,169 @@
+/*
+ * evok.h -- C ABI of libevok.so: the sm_100a kernels behind the per-generation hot path of
+ * EvoTorch's distribution-based searchers (PGPE / SNES / CEM / XNES / CMA-ES).
+ *
+ * The reference (nnaisense/evotorch @ cebcac4f) has no FFI: its "plugin interface" on this path is a
+ * set of Python methods whose bodies are sequences of torch ops.  Each entry point below replaces the
+ * body of one of those methods; the citation is `path:line` under /root/reference/src/evotorch.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add at each site.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller owns all memory, including workspaces (query the *_workspace_bytes functions);
+ *     the library never allocates, frees or synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, so every call is
+ *     CUDA-graph capturable and re-entrant;
+ *   - return value: 0 = ok, negative = argument error (EVOK_E_*), positive = cudaError_t;
+ *   - populations are row-major fp32: X[i * ldx + j], i < n_rows, j < D.
+ */
+#ifndef EVOK_H_
+#define EVOK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVOK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EVOK_API __attribute__((visibility("default")))
+#else
+#define EVOK_API
+#endif
+
+/* argument-error codes (negative return values) */
+#define EVOK_E_NULLPTR (-1)
+#define EVOK_E_BADSIZE (-2)
+#define EVOK_E_BADENUM (-3)
+#define EVOK_E_WORKSPACE (-4)
+#define EVOK_E_ODDROWS (-5) /* symmetric sampling / gradients need an even number of rows */
+#define EVOK_E_ALIGN (-6)
+
+/* objective functions with a fused evaluation kernel */
+#define EVOK_OBJ_NONE 0      /* sample only */
+#define EVOK_OBJ_SPHERE 1    /* sum x^2 */
+#define EVOK_OBJ_RASTRIGIN 2 /* 10 D + sum(x^2 - 10 cos(2 pi x))  (reference README.md:86-89) */
+#define EVOK_OBJ_ACKLEY 3    /* -20 exp(-0.2 sqrt(mean x^2)) - exp(mean cos(2 pi x)) + 20 + e */
+#define EVOK_OBJ_COUNT 4
+
+/* ranking methods (tools/ranking.py:186) */
+#define EVOK_RANK_CENTERED 0
+#define EVOK_RANK_LINEAR 1
+#define EVOK_RANK_NES 2
+#define EVOK_RANK_NORMALIZED 3
+#define EVOK_RANK_RAW 4
+
+/* gradient forms: S1_j = sum_r a_r eps_rj ; S2_j = sum_r b_r g(eps_rj) */
+#define EVOK_GRAD_SEPARABLE 0 /* g = (eps^2 - sigma^2)/sigma; a=b=w_i; all rows      (distributions.py:548-579) */
+#define EVOK_GRAD_SYMMETRIC 1 /* same g; a,b = (w+ -/+ w-)/2; even rows only           (distributions.py:708-773) */
+#define EVOK_GRAD_EXP 2       /* g = (eps/sigma)^2 - 1; a=b=w_i                        (distributions.py:783-793) */
+#define EVOK_GRAD_MOMENTS 3   /* g = eps^2; a=b=w_i (0/1 elite mask for CEM)           (distributions.py:538-546) */
+
+int evok_abi_version(void);
+const char* evok_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 / K2: population sampling and evaluation.
+ * Replaces: Distribution.sample -> SymmetricSeparableGaussian._fill / SeparableGaussian._fill
+ *           (distributions.py:155-216, :514, :705) -> make_gaussian (tools/misc.py:1663-1755), and, for the
+ *           built-in objectives, Problem._evaluate_batch (core.py:2602-2608).
+ * Random numbers: Philox4x32-10 keyed by `seed`; the counter of a draw is a pure function of
+ * (global row or direction index, column, `stream_id`), so the population does not depend on the launch
+ * geometry nor on how rows are sharded over GPUs (`row0` = global index of the first local row).
+ * symmetric != 0: rows 2k and 2k+1 are mu + sigma*z_k and mu - sigma*z_k (row0 and n_rows even).
+ * X may be NULL when objective != NONE ("lazy population": evaluate without materialising).
+ * f may be NULL when objective == NONE.
+ * --------------------------------------------------------------------------------------------- */
+int evok_sample_eval(int objective, float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0,
+                     int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, float* f,
+                     void* stream);
+
+/* K2 alone: f[i] = objective(X[i, :]) for an already materialised population (torch-RNG parity mode,
+ * CMA-ES / XNES populations).  Replaces the user's vectorised torch objective at core.py:2604. */
+int evok_eval(int objective, const float* X, int64_t ldx, int64_t n_rows, int64_t D, float* f, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3: fitness -> utilities.  Replaces tools/ranking.py:24-183 (`rank` :189).
+ * Sort semantics: STABLE (equal fitnesses keep ascending index order), -0 == +0, NaN largest;
+ * identical to torch.argsort(f, descending=!higher_is_better, stable=True).
+ * w: utilities (same length).  perm (nullable): the sorted order, worst first, as int64 (what
+ * `argsort` returns).  ws: workspace of at least evok_rank_workspace_bytes(N) bytes.
+ * --------------------------------------------------------------------------------------------- */
+size_t evok_rank_workspace_bytes(int64_t N);
+int evok_rank(int method, const float* f, int64_t N, int higher_is_better, float* w, int64_t* perm, void* ws,
+              size_t ws_bytes, void* stream);
+
+/* Stable argsort of fp32 keys (SolutionBatch.argsort core.py:3827, CEM elite selection distributions.py:541,
+ * CMA-ES cmaes.py:445).  Same workspace as evok_rank. */
+int evok_argsort(const float* keys, int64_t N, int descending, int64_t* perm, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* In-place weight post-processing on the N-vector (distributions.py:562-563, :722-723 `w - mean(w)`;
+ * :784-785 `w / sum|w|`).  mode 1: subtract mean; mode 2: divide by sum of absolute values. */
+int evok_weights_adjust(float* w, int64_t N, int mode, void* stream);
+
+/* 0/1 mask of the `num_elites` largest weights, ties broken by ascending index (distributions.py:540-542).
+ * Needs the rank workspace. */
+int evok_elite_mask(const float* w, int64_t N, int64_t num_elites, float* mask, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4: utility-weighted column reductions over the population.
+ * Replaces SeparableGaussian._compute_gradients (distributions.py:548-579),
+ * SymmetricSeparableGaussian._compute_gradients (:708-773), ExpSeparableGaussian._compute_gradients
+ * (:783-793) and the elite moments of _compute_gradients_via_parenthood_ratio (:538-546).
+ *   out_mu[j]    = scale_mu    * sum_r a_r * (X[r,j] - mu[j])
+ *   out_sigma[j] = scale_sigma * sum_r b_r * g(X[r,j] - mu[j])          (g, a, b per `form` above)
+ * `w` holds the weights of the n_rows local rows (a slice of the global utility vector when the
+ * population is sharded; the partial results of the shards then add up: all-reduce(sum)).
+ * Deterministic (fixed two-stage reduction order, no atomics).
+ * --------------------------------------------------------------------------------------------- */
+size_t evok_grad_workspace_bytes(int64_t n_rows, int64_t D);
+int evok_grad(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma,
+              int64_t n_rows, int64_t D, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* K4 without a materialised population: regenerates eps from the Philox counters used by
+ * evok_sample_eval(..., X = NULL) with the same (seed, stream_id, row0). */
+int evok_grad_regen(int form, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
+                    int64_t D, uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu,
+                    float* out_sigma, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5: D-vector updates (no host synchronisation; norms are reduced on the device).
+ * --------------------------------------------------------------------------------------------- */
+/* ClipUp.ascent (optimizers.py:319-357): v <- clip(momentum*v + stepsize*g/||g||, max_speed).
+ * velocity is updated in place; step_out (nullable) receives the ascent step; mu (nullable) += step. */
+int evok_clipup_step(const float* g, int64_t D, float* velocity, float stepsize, float momentum, float max_speed,
+                     float* step_out, float* mu, void* stream);
+/* Adam via TorchOptimizer.ascent (optimizers.py:60-91, :101-165): m, v updated in place; `t` is the 1-based
+ * step count; step = lr * m_hat / (sqrt(v_hat) + eps). */
+int evok_adam_step(const float* g, int64_t D, float* m, float* v, int64_t t, float lr, float beta1, float beta2,
+                   float eps, float* step_out, float* mu, void* stream);
+/* SGD with optional momentum (optimizers.py:168-228): buf <- momentum*buf + g (first step: buf = g). */
+int evok_sgd_step(const float* g, int64_t D, float* buf, int first_step, float lr, float momentum, float* step_out,
+                  float* mu, void* stream);
+/* mu += lr * g  (Distribution._follow_gradient with a plain learning rate, distributions.py:385). */
+int evok_axpy(const float* g, int64_t D, float lr, float* mu, void* stream);
+
+/* sigma update + controlled clamp.  Replaces distributions.py:591-596 / :805-808 and modify_tensor
+ * (tools/misc.py:711-816) as used by gaussian.py:404-416.
+ *   exp_form == 0: target = sigma + lr*g          exp_form != 0: target = sigma * exp(0.5*lr*g)
+ *   lo = max(lb, sigma - |sigma|*mc), hi = min(ub, sigma + |sigma|*mc); sigma <- min(max(target, lo), hi)
+ * lb / ub / mc: device vectors (length D) or NULL; when NULL the scalar is used; a NaN scalar means
+ * "not set" (-inf / +inf / no max-change limit). */
+int evok_sigma_update(float* sigma, const float* g, int64_t D, float lr, int exp_form, const float* lb_vec,
+                      float lb, const float* ub_vec, float ub, const float* mc_vec, float mc, void* stream);
+
+/* CEM finalisation from elite moments (distributions.py:543-546): given S1 = sum eps, S2 = sum eps^2 over
+ * the E elites, writes grad_mu = S1/E and grad_sigma = sqrt((S2 - S1^2/E)/(E-1)) - sigma. */
+int evok_cem_finalize(const float* s1, const float* s2, const float* sigma, int64_t D, int64_t num_elites,
+                      float* grad_mu, float* grad_sigma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOK_H_ */

@@ -1,0 +1,237 @@
+"""The host-side mirror of the reference API on CPU tensors (BASELINE config 1 path): seeded trajectories of the package
+must reproduce the REAL reference's trajectories recorded in tests/golden (same torch RNG stream => same populations)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from evotorch_b200 import Problem, SolutionBatch
+from evotorch_b200.algorithms import CEM, PGPE, SNES, XNES
+from evotorch_b200.distributions import ExpSeparableGaussian, SeparableGaussian, SymmetricSeparableGaussian
+from evotorch_b200.logging import PandasLogger, StdOutLogger
+from evotorch_b200.optimizers import SGD, Adam, ClipUp, get_optimizer_class
+from evotorch_b200.tools import modify_tensor, rank
+
+
+def rastrigin(x: torch.Tensor) -> torch.Tensor:
+    n = x.shape[1]
+    return 10 * n + torch.sum((x**2) - 10 * torch.cos(2 * np.pi * x), 1)
+
+
+def sphere(x: torch.Tensor) -> torch.Tensor:
+    return torch.sum(x**2, dim=-1)
+
+
+def T(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32)
+
+
+MAKERS = {
+    "pgpe": (lambda p: PGPE(p, popsize=32, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0), 8, "min", rastrigin),
+    "pgpe_max": (lambda p: PGPE(p, popsize=32, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0), 8, "max", rastrigin),
+    "pgpe_nonsym_adam": (lambda p: PGPE(p, popsize=30, center_learning_rate=0.05, stdev_learning_rate=0.1, stdev_init=1.0,
+                                         symmetric=False, optimizer="adam"), 8, "min", rastrigin),
+    "pgpe_nes_rank": (lambda p: PGPE(p, popsize=32, center_learning_rate=0.3, stdev_learning_rate=0.1, radius_init=4.0,
+                                      ranking_method="nes", optimizer=None, stdev_min=0.01, stdev_max=2.0), 8, "min", rastrigin),
+    "snes": (lambda p: SNES(p, popsize=24, stdev_init=2.0), 8, "min", rastrigin),
+    "snes_clipup": (lambda p: SNES(p, popsize=24, stdev_init=2.0, optimizer="clipup", center_learning_rate=0.2,
+                                    stdev_max_change=0.3), 8, "min", rastrigin),
+    "cem": (lambda p: CEM(p, popsize=40, parenthood_ratio=0.25, stdev_init=2.0, stdev_max_change=0.5), 8, "min", rastrigin),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(MAKERS))
+def test_cpu_trajectory_matches_reference(golden, tag):
+    make, D, sense, fn = MAKERS[tag]
+    prob = Problem(sense, fn, initial_bounds=(-5.12, 5.12), solution_length=D, vectorized=True, seed=11, dtype=torch.float32)
+    s = make(prob)
+    mus, sigs = golden[f"traj/{tag}/mu"], golden[f"traj/{tag}/sigma"]
+    for t in range(len(mus)):
+        s.step()
+        np.testing.assert_allclose(s.status["center"].numpy(), mus[t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(s.status["stdev"].numpy(), sigs[t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(s.population.values.numpy(), golden[f"traj/{tag}/X"][t], rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(s.population.evals[:, 0].numpy(), golden[f"traj/{tag}/f"][t], rtol=1e-5, atol=1e-4)
+    assert s.step_count == len(mus) and s.status["iter"] == len(mus)
+    for key in ("best", "worst", "best_eval", "worst_eval", "center", "stdev", "mean_eval", "pop_best", "pop_best_eval", "median_eval"):
+        assert key in s.status
+    assert math.isfinite(s.status["mean_eval"]) and math.isfinite(s.status["pop_best_eval"])
+
+
+def test_xnes_cpu_trajectory(golden):
+    prob = Problem("min", sphere, initial_bounds=(-5.12, 5.12), solution_length=5, vectorized=True, seed=11, dtype=torch.float32)
+    s = XNES(prob, popsize=16, stdev_init=1.5)
+    for t in range(5):
+        s.step()
+        np.testing.assert_allclose(s.status["center"].numpy(), golden["traj/xnes/mu"][t], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(s.status["stdev"].numpy(), golden["traj/xnes/sigma"][t], rtol=2e-4, atol=2e-5)
+
+
+def test_readme_snes_config1_runs_on_cpu():
+    # BASELINE.json configs[0]: SNES, Rastrigin, dim=100, popsize=1000, CPU (reference README.md:76-116)
+    prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=100, vectorized=True, seed=1)
+    s = SNES(prob, popsize=1000, stdev_init=10.0)
+    log = PandasLogger(s)
+    s.run(30)
+    df = log.to_dataframe()
+    assert len(df) == 30 and df["mean_eval"].iloc[-1] < df["mean_eval"].iloc[0]
+
+
+@pytest.mark.parametrize("method", ["centered", "linear", "nes", "normalized", "raw"])
+@pytest.mark.parametrize("name", ["appxB", "rand257", "rand1000", "tied600"])
+def test_rank_cpu_matches_reference(golden, method, name):
+    f = T(golden[f"rank/{name}/f"])
+    for hib in (True, False):
+        got = rank(f, method, higher_is_better=hib).numpy()
+        np.testing.assert_allclose(got, golden[f"rank/{name}/{method}/{int(hib)}"], rtol=3e-6, atol=3e-7)
+    with pytest.raises(KeyError):
+        rank(f, "nope", higher_is_better=True)
+
+
+def test_distribution_api_and_errors(golden):
+    mu, sg = T(golden["grad/mu"]), T(golden["grad/sigma"])
+    d = SymmetricSeparableGaussian({"mu": mu, "sigma": sg, "divide_mu_grad_by": "num_directions", "divide_sigma_grad_by": "num_directions"})
+    g = d.compute_gradients(T(golden["grad/Xsym"]), T(golden["grad/fsym"]), objective_sense="min", ranking_method="centered")
+    np.testing.assert_allclose(g["mu"].numpy(), golden["grad/sym/centered/min/num_directions/mu"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(g["sigma"].numpy(), golden["grad/sym/centered/min/num_directions/sigma"], rtol=2e-4, atol=2e-6)
+    with pytest.raises(ValueError):
+        d.compute_gradients(T(golden["grad/Xsym"]), T(golden["grad/fsym"]), objective_sense="up")
+    with pytest.raises(ValueError):
+        d.compute_gradients(T(golden["grad/Xsym"]), T(golden["grad/fsym"][:-1]), objective_sense="min")
+    with pytest.raises(ValueError):
+        d.sample(out=torch.empty(4, 3))
+    with pytest.raises(ValueError):
+        d.sample(out=torch.empty(5, 16))  # odd number of rows for a symmetric distribution
+    with pytest.raises(ValueError):
+        d.sample(4, out=torch.empty(4, 16))
+    with pytest.raises(ValueError):
+        SeparableGaussian({"mu": mu, "sigma": sg, "bogus": 1})
+    x = d.sample(6, generator=torch.Generator().manual_seed(0))
+    np.testing.assert_allclose((x[0::2] + x[1::2]).numpy(), np.broadcast_to(2 * mu.numpy(), (3, 16)), atol=1e-5)
+    upd = d.update_parameters(g, learning_rates={"mu": 0.1, "sigma": 0.2})
+    assert upd is not d and torch.equal(d.mu, mu)
+    np.testing.assert_allclose(upd.mu.numpy(), (mu + 0.1 * g["mu"]).numpy(), rtol=1e-6)
+    e = ExpSeparableGaussian({"mu": mu, "sigma": sg})
+    ge = e.compute_gradients(T(golden["grad/Xns"]), T(golden["grad/fns"]), objective_sense="max", ranking_method="centered")
+    np.testing.assert_allclose(ge["sigma"].numpy(), golden["grad/exp/centered/max/sigma"], rtol=2e-4, atol=5e-5)
+    for ratio in (0.5, 0.25, 0.1):
+        c = SeparableGaussian({"mu": mu, "sigma": sg, "parenthood_ratio": ratio})
+        gc = c.compute_gradients(T(golden["grad/Xns"]), T(golden["grad/fns"]), objective_sense="min", ranking_method=None)
+        np.testing.assert_allclose(gc["mu"].numpy(), golden[f"grad/cem/{ratio}/min/mu"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(gc["sigma"].numpy(), golden[f"grad/cem/{ratio}/min/sigma"], rtol=1e-4, atol=5e-6)
+
+
+def test_partial_gradients_add_up(golden):
+    mu, sg = T(golden["grad/mu"]), T(golden["grad/sigma"])
+    X, f = T(golden["grad/Xsym"]), T(golden["grad/fsym"])
+    for cls, extra, method in ((SymmetricSeparableGaussian, {"divide_mu_grad_by": "num_directions", "divide_sigma_grad_by": "num_directions"}, "nes"),
+                               (SeparableGaussian, {"parenthood_ratio": 0.25}, "raw"), (ExpSeparableGaussian, {}, "centered")):
+        d = cls({"mu": mu, "sigma": sg, **extra})
+        w = rank(f, method, higher_is_better=False)
+        whole = d._compute_gradients(X, w, method)
+        parts = [d.partial_gradients(X[a:b], w, a, method) for a, b in ((0, 20), (20, 44), (44, 64))]
+        summed = {k: sum(p[k] for p in parts) for k in parts[0]}
+        fin = d.finalize_gradients(summed, 64)
+        for k in whole:
+            np.testing.assert_allclose(fin[k].numpy(), whole[k].numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_optimizers_cpu(golden):
+    grads = golden["opt/grads"]
+    for i in range(4):
+        ss, mom, ms = golden[f"opt/clipup/{i}/cfg"]
+        opt = ClipUp(solution_length=12, dtype="float32", stepsize=ss, momentum=mom, max_speed=None if ms < 0 else ms)
+        got = np.stack([opt.ascent(T(g)).numpy() for g in grads])
+        np.testing.assert_allclose(got, golden[f"opt/clipup/{i}/steps"], rtol=2e-6, atol=2e-7)
+    opt = Adam(solution_length=12, dtype="float32", stepsize=0.05)
+    np.testing.assert_allclose(np.stack([opt.ascent(T(g)).numpy() for g in grads]), golden["opt/adam/0/steps"], rtol=5e-6, atol=1e-7)
+    opt = SGD(solution_length=12, dtype="float32", stepsize=0.1, momentum=0.8)
+    np.testing.assert_allclose(np.stack([opt.ascent(T(g)).numpy() for g in grads]), golden["opt/sgd/1/steps"], rtol=2e-6, atol=1e-7)
+    # API validation mirrored from the reference's tests/test_optimizers.py:25-43, :115-138
+    with pytest.raises(ValueError):
+        ClipUp(solution_length=3, dtype="float32", stepsize=-1.0)
+    with pytest.raises(ValueError):
+        ClipUp(solution_length=3, dtype="float32", stepsize=0.1, momentum=1.5)
+    with pytest.raises(ValueError):
+        Adam(solution_length=3, dtype="float32", beta1=0.9)
+    c = ClipUp(solution_length=3, dtype="float32", stepsize=0.1)
+    assert c.param_groups[0]["max_speed"] == pytest.approx(0.2)
+    c.param_groups[0]["lr"] = 0.3
+    assert c.param_groups[0]["lr"] == 0.3
+    with pytest.raises(ValueError):
+        c.param_groups[0]["momentum"] = 2.0
+    assert get_optimizer_class("clipup") is ClipUp and get_optimizer_class("adam") is Adam and get_optimizer_class("sga") is SGD
+    assert get_optimizer_class("clipup", {"max_speed": 0.7})(solution_length=2, dtype="float32", stepsize=0.1).param_groups[0]["max_speed"] == 0.7
+    with pytest.raises(ValueError):
+        get_optimizer_class("nope")
+
+
+def test_modify_tensor_known_answers():
+    x, t = T([10, 11, 12]), T([0, 21, 22])
+    assert modify_tensor(x, t, lb=5).tolist() == [5, 21, 22]
+    assert modify_tensor(x, t, lb=5, ub=20).tolist() == [5, 20, 20]
+    assert modify_tensor(x, t, max_change=0.5).tolist() == [5, 16.5, 18]
+    assert modify_tensor(x, t, lb=7, ub=17, max_change=0.5).tolist() == [7, 16.5, 17]
+    with pytest.raises(IndexError):
+        modify_tensor(x, t, lb=T([1, 2]))
+
+
+def test_solution_batch_semantics():
+    prob = Problem("max", sphere, initial_bounds=(-1, 1), solution_length=4, vectorized=True, seed=3, eval_data_length=2)
+    b = SolutionBatch(prob, 6)
+    assert b.values.shape == (6, 4) and b.evals.shape == (6, 3) and torch.isnan(b.evals).all()
+    assert float(b.values.min()) >= -1 and float(b.values.max()) <= 1
+    prob.evaluate(b)
+    assert not torch.isnan(b.evals[:, 0]).any() and torch.isnan(b.evals[:, 1:]).all()
+    assert int(b.argbest()) == int(torch.argmax(b.evals[:, 0])) and int(b.argworst()) == int(torch.argmin(b.evals[:, 0]))
+    assert b.argsort().tolist() == torch.argsort(b.evals[:, 0], descending=True, stable=True).tolist()
+    v = b.access_values(keep_evals=True)
+    assert not torch.isnan(b.evals[:, 0]).any()
+    v = b.access_values()
+    assert torch.isnan(b.evals).all() and v.data_ptr() == b.values.data_ptr()
+    b.set_evals(torch.arange(6.0), torch.ones(6, 2))
+    assert b.evals[:, 0].tolist() == [0, 1, 2, 3, 4, 5] and b[2].evals.tolist() == [2, 1, 1]
+    s = b[5].clone()
+    b.set_values(torch.zeros(6, 4))
+    assert torch.isnan(b.evals).all() and s.evals[0] == 5 and s.is_evaluated and not b[0].is_evaluated
+    pieces = b.split(4)
+    assert [len(p) for p in pieces] == [2, 2, 1, 1] and pieces[0].values.data_ptr() == b.values.data_ptr()
+    assert len(SolutionBatch.cat(pieces)) == 6
+    with pytest.raises(ValueError):
+        b.set_evals(torch.zeros(5))
+    with pytest.raises(NotImplementedError):
+        Problem("min", sphere, solution_length=3, num_actors=4)
+    with pytest.raises(ValueError):
+        Problem("sideways", sphere, solution_length=3)
+    bounded = Problem("min", sphere, bounds=(-1, 1), solution_length=3, vectorized=True)
+    with pytest.raises(ValueError):
+        SNES(bounded, stdev_init=1.0)
+    with pytest.raises(ValueError):
+        PGPE(prob, popsize=7, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0)
+    with pytest.raises(ValueError):
+        PGPE(prob, popsize=8, center_learning_rate=0.1, stdev_learning_rate=0.1)
+
+
+def test_builtin_objectives_on_cpu(golden):
+    from evotorch_b200.objectives import ackley, rastrigin as rb, sphere as sb
+
+    X = T(golden["grad/Xsym"])
+    np.testing.assert_allclose(rb(X).numpy(), golden["grad/fsym"], rtol=1e-6)
+    np.testing.assert_allclose(sb(X).numpy(), (X**2).sum(1).numpy(), rtol=1e-6)
+    assert ackley(torch.zeros(2, 5)).abs().max() < 1e-5
+    assert rb.evok_objective_id == 2 and rb.__evotorch_vectorized__
+    prob = Problem("min", rb, initial_bounds=(-5.12, 5.12), solution_length=8, seed=11)
+    s = PGPE(prob, popsize=32, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+    s.run(3)
+    np.testing.assert_allclose(s.status["center"].numpy(), golden["traj/pgpe/mu"][2], rtol=1e-5, atol=2e-6)
+
+
+def test_stdout_logger(capsys):
+    prob = Problem("min", sphere, initial_bounds=(-1, 1), solution_length=4, vectorized=True, seed=3)
+    s = SNES(prob, stdev_init=1.0)
+    StdOutLogger(s, interval=2)
+    s.run(4)
+    out = capsys.readouterr().out
+    assert out.count("iter") == 2 and "mean_eval" in out
