@@ -21,6 +21,7 @@ _P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
     "evok_abi_version": (c_int, []),
+    "evok_launch_count": (c_uint64, []),
     "evok_error_string": (ctypes.c_char_p, [c_int]),
     "evok_sample_eval": (c_int, [c_int, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint64, _P, _P]),
     "evok_eval": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P]),

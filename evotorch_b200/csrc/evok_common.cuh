@@ -6,13 +6,19 @@
 
 #include "../../include/evok.h"
 
-#define EVOK_CHECK_LAUNCH()                          \
+#define EVOK_CHECK_LAUNCH_N(n)                       \
   do {                                               \
     cudaError_t e__ = cudaPeekAtLastError();         \
     if (e__ != cudaSuccess) return (int)e__;         \
+    evok::count_launches(n);                         \
   } while (0)
+#define EVOK_CHECK_LAUNCH() EVOK_CHECK_LAUNCH_N(1)
 
 namespace evok {
+
+// number of kernels this library has launched (exposed as evok_launch_count(); bench.py reports it)
+extern unsigned long long g_launch_count;
+inline void count_launches(int n) { __atomic_fetch_add(&g_launch_count, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200

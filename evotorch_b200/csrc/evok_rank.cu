@@ -284,7 +284,7 @@ static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const
     radix_hist_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], N, shift, counts, p.n_tiles);
     digit_scan_kernel<<<kRadix, 256, 0, st>>>(counts, p.n_tiles, totals);
     radix_scatter_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
-    EVOK_CHECK_LAUNCH();
+    EVOK_CHECK_LAUNCH_N(3);
     cur ^= 1;
   }
   *sorted_idx = idx[cur];
@@ -315,7 +315,7 @@ extern "C" EVOK_API int evok_rank(int method, const float* f, int64_t N, int hig
     const float sign = higher_is_better ? 1.0f : -1.0f;
     if (method == EVOK_RANK_NORMALIZED) mean_std_kernel<<<1, 1024, 0, st>>>(f, N, sign, scalar);
     affine_kernel<<<nb, 256, 0, st>>>(f, N, sign, scalar, method == EVOK_RANK_NORMALIZED, w);
-    EVOK_CHECK_LAUNCH();
+    EVOK_CHECK_LAUNCH_N(method == EVOK_RANK_NORMALIZED ? 2 : 1);
     if (perm) {
       uint32_t* sidx = nullptr;
       int rc = sort_pairs(f, N, !higher_is_better, ws, p, st, &sidx);
@@ -330,7 +330,7 @@ extern "C" EVOK_API int evok_rank(int method, const float* f, int64_t N, int hig
   if (rc) return rc;
   if (method == EVOK_RANK_NES) nes_table_sum_kernel<<<1, 1024, 0, st>>>(N, scalar);
   scatter_utilities_kernel<<<nb, 256, 0, st>>>(sidx, N, method, scalar, w, perm);
-  EVOK_CHECK_LAUNCH();
+  EVOK_CHECK_LAUNCH_N(method == EVOK_RANK_NES ? 2 : 1);
   return 0;
 }
 

@@ -5,6 +5,8 @@
 
 namespace evok {
 
+unsigned long long g_launch_count = 0;
+
 constexpr int kUpdThreads = 1024;
 
 __global__ void __launch_bounds__(kUpdThreads) clipup_kernel(const float* __restrict__ g, int64_t D, float* __restrict__ velocity,
@@ -172,6 +174,8 @@ extern "C" EVOK_API int evok_cem_finalize(const float* s1, const float* s2, cons
 }
 
 extern "C" EVOK_API int evok_abi_version(void) { return EVOK_ABI_VERSION; }
+
+extern "C" EVOK_API uint64_t evok_launch_count(void) { return (uint64_t)__atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 extern "C" EVOK_API const char* evok_error_string(int code) {
   switch (code) {

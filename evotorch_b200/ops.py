@@ -21,6 +21,56 @@ GRAD_SEPARABLE, GRAD_SYMMETRIC, GRAD_EXP, GRAD_MOMENTS = 0, 1, 2, 3
 NAN = float("nan")
 
 
+# ------------------------------------------------------------------------------------------------ device-side kernel timers
+# bench.py turns these on to time each kernel group with CUDA events recorded on the launching stream (no host sync while
+# the generations run; the elapsed times are read after the timed region).
+_timers: Optional[dict] = None
+
+
+def enable_timers() -> None:
+    global _timers
+    _timers = {}
+
+
+def disable_timers() -> None:
+    global _timers
+    _timers = None
+
+
+class _timed:
+    __slots__ = ("name", "start")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _timers is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timers is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _timers.setdefault(self.name, []).append((self.start, end))
+        return False
+
+
+def timer_results() -> dict:
+    """{kernel group: (launch count, mean milliseconds)}; call after torch.cuda.synchronize()."""
+    out = {}
+    for name, pairs in (_timers or {}).items():
+        ms = [a.elapsed_time(b) for a, b in pairs]
+        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out
+
+
+def launch_count() -> int:
+    """Kernels launched by libevok.so so far in this process (exact: counted inside the library)."""
+    return int(nat.lib().evok_launch_count())
+
+
 def uses_kernels(t: torch.Tensor) -> bool:
     """True for the tensors the hand-written kernels handle: CUDA + float32."""
     return t.is_cuda and t.dtype == torch.float32
@@ -53,8 +103,9 @@ def sample_eval(objective: int, X: Optional[torch.Tensor], mu: torch.Tensor, sig
         ldx = X.stride(0)
     if f is not None:
         _vec(f, "f", n_rows)
-    rc = nat.lib().evok_sample_eval(objective, nat.ptr(X), ldx, mu.data_ptr(), sigma.data_ptr(), row0, n_rows, D, int(symmetric),
-                                    seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, nat.ptr(f), nat.stream_of(mu))
+    with _timed("sample_eval" if objective != OBJ_NONE else "sample"):
+        rc = nat.lib().evok_sample_eval(objective, nat.ptr(X), ldx, mu.data_ptr(), sigma.data_ptr(), row0, n_rows, D, int(symmetric),
+                                        seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, nat.ptr(f), nat.stream_of(mu))
     nat.check(rc, "evok_sample_eval")
 
 
@@ -64,7 +115,9 @@ def evaluate(objective: int, X: torch.Tensor, f: Optional[torch.Tensor] = None) 
     if f is None:
         f = torch.empty(n, dtype=torch.float32, device=X.device)
     _vec(f, "f", n)
-    nat.check(nat.lib().evok_eval(objective, X.data_ptr(), X.stride(0), n, D, f.data_ptr(), nat.stream_of(X)), "evok_eval")
+    with _timed("eval"):
+        rc = nat.lib().evok_eval(objective, X.data_ptr(), X.stride(0), n, D, f.data_ptr(), nat.stream_of(X))
+    nat.check(rc, "evok_eval")
     return f
 
 
@@ -81,8 +134,10 @@ def rank(f: torch.Tensor, method: str, higher_is_better: bool, out: Optional[tor
     if perm is not None and not (perm.is_cuda and perm.dtype == torch.int64 and perm.is_contiguous() and perm.numel() == n):
         raise ValueError("perm: expected a contiguous int64 CUDA tensor of the same length")
     ws = _rank_ws(f.device, n)
-    rc = nat.lib().evok_rank(RANK_IDS[method], f.data_ptr(), n, int(bool(higher_is_better)), w.data_ptr(), nat.ptr(perm), ws.data_ptr(),
-                             ws.numel(), nat.stream_of(f))
+    method_id = RANK_IDS[method]
+    with _timed("rank"):
+        rc = nat.lib().evok_rank(method_id, f.data_ptr(), n, int(bool(higher_is_better)), w.data_ptr(), nat.ptr(perm), ws.data_ptr(),
+                                 ws.numel(), nat.stream_of(f))
     nat.check(rc, "evok_rank")
     return w
 
@@ -122,8 +177,9 @@ def grad(form: int, X: torch.Tensor, w: torch.Tensor, mu: torch.Tensor, sigma: t
     out_mu = torch.empty_like(mu) if out_mu is None else _vec(out_mu, "out_mu", D)
     out_sigma = torch.empty_like(mu) if out_sigma is None else _vec(out_sigma, "out_sigma", D)
     ws = nat.workspace(X.device, nat.lib().evok_grad_workspace_bytes(n, D), "grad")
-    rc = nat.lib().evok_grad(form, X.data_ptr(), X.stride(0), w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), n, D, scale_mu, scale_sigma,
-                             out_mu.data_ptr(), out_sigma.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(X))
+    with _timed("grad"):
+        rc = nat.lib().evok_grad(form, X.data_ptr(), X.stride(0), w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), n, D, scale_mu,
+                                 scale_sigma, out_mu.data_ptr(), out_sigma.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(X))
     nat.check(rc, "evok_grad")
     return out_mu, out_sigma
 
@@ -136,9 +192,10 @@ def grad_regen(form: int, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor
     out_mu = torch.empty_like(mu) if out_mu is None else _vec(out_mu, "out_mu", D)
     out_sigma = torch.empty_like(mu) if out_sigma is None else _vec(out_sigma, "out_sigma", D)
     ws = nat.workspace(mu.device, nat.lib().evok_grad_workspace_bytes(n, D), "grad")
-    rc = nat.lib().evok_grad_regen(form, w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), row0, n, D, seed & 0xFFFFFFFFFFFFFFFF,
-                                   stream_id & 0xFFFFFFFFFFFFFFFF, scale_mu, scale_sigma, out_mu.data_ptr(), out_sigma.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), nat.stream_of(mu))
+    with _timed("grad_regen"):
+        rc = nat.lib().evok_grad_regen(form, w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), row0, n, D, seed & 0xFFFFFFFFFFFFFFFF,
+                                       stream_id & 0xFFFFFFFFFFFFFFFF, scale_mu, scale_sigma, out_mu.data_ptr(), out_sigma.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), nat.stream_of(mu))
     nat.check(rc, "evok_grad_regen")
     return out_mu, out_sigma
 
@@ -148,8 +205,9 @@ def clipup_step(g: torch.Tensor, velocity: torch.Tensor, stepsize: float, moment
                 step_out: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None) -> None:
     D = g.numel()
     _vec(g, "g"); _vec(velocity, "velocity", D)
-    rc = nat.lib().evok_clipup_step(g.data_ptr(), D, velocity.data_ptr(), stepsize, momentum, max_speed, nat.ptr(step_out), nat.ptr(mu),
-                                    nat.stream_of(g))
+    with _timed("mu_step"):
+        rc = nat.lib().evok_clipup_step(g.data_ptr(), D, velocity.data_ptr(), stepsize, momentum, max_speed, nat.ptr(step_out),
+                                        nat.ptr(mu), nat.stream_of(g))
     nat.check(rc, "evok_clipup_step")
 
 
@@ -195,8 +253,9 @@ def sigma_update_(sigma: torch.Tensor, g: torch.Tensor, lr: float, exp_form: boo
     lbv, lbs = _bound(lb, D, sigma.device)
     ubv, ubs = _bound(ub, D, sigma.device)
     mcv, mcs = _bound(max_change, D, sigma.device)
-    rc = nat.lib().evok_sigma_update(sigma.data_ptr(), g.data_ptr(), D, lr, int(exp_form), nat.ptr(lbv), lbs, nat.ptr(ubv), ubs,
-                                     nat.ptr(mcv), mcs, nat.stream_of(sigma))
+    with _timed("sigma_step"):
+        rc = nat.lib().evok_sigma_update(sigma.data_ptr(), g.data_ptr(), D, lr, int(exp_form), nat.ptr(lbv), lbs, nat.ptr(ubv), ubs,
+                                         nat.ptr(mcv), mcs, nat.stream_of(sigma))
     nat.check(rc, "evok_sigma_update")
 
 

@@ -63,6 +63,8 @@ extern "C" {
 #define EVOK_GRAD_MOMENTS 3   /* g = eps^2; a=b=w_i (0/1 elite mask for CEM)           (distributions.py:538-546) */
 
 int evok_abi_version(void);
+/* number of kernels launched by this library since it was loaded (for bench.py's gpu_launches) */
+uint64_t evok_launch_count(void);
 const char* evok_error_string(int code);
 
 /* ---------------------------------------------------------------------------------------------

@@ -615,3 +615,70 @@ def mlp_policy_forward(params, obs, n_in: int, n_hidden: int, n_out: int, activa
     elif activation != "none":
         raise ValueError(activation)
     return (np.einsum("noh,nh->no", W2, h) + b2).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# The kernels' Philox4x32-10 sampler (include/evok.h, evok_sample_eval).  Not part of the reference
+# (which draws from torch's generator, tools/misc.py:1739): this restates the NEW engine's documented
+# counter mapping so the GPU tests can check it (geometry / shard independence, known-answer vectors of
+# Random123's philox4x32-10).
+# --------------------------------------------------------------------------------------
+
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int) -> tuple:
+    """Vectorised Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11).  Counters are uint32 arrays, keys python ints."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _MASK32 for c in (c0, c1, c2, c3))
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c0
+        p1 = _PHILOX_M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def _box_muller(a: np.ndarray, b: np.ndarray) -> tuple:
+    u1 = a.astype(np.float64) * 2.0**-32 + 2.0**-33
+    th = 2.0 * math.pi * (b.astype(np.float64) * 2.0**-32 + 2.0**-33)
+    r = np.sqrt(-2.0 * np.log(u1))
+    return r * np.cos(th), r * np.sin(th)
+
+
+def philox_normals(seed: int, stream_id: int, units: np.ndarray, D: int) -> np.ndarray:
+    """Standard normals z[unit, column] of the kernels' sampler (float64; the kernels use fast fp32 intrinsics, so
+    compare with ~1e-5 absolute tolerance).  counter = (column // 4, unit_lo, unit_hi, stream_id_lo),
+    key = (seed_lo, seed_hi ^ stream_id_hi); outputs (x, y) -> columns 4q, 4q+1 and (z, w) -> 4q+2, 4q+3."""
+    units = np.asarray(units, dtype=np.uint64)
+    nq = (D + 3) // 4
+    q = np.arange(nq, dtype=np.uint64)
+    U, Q = np.meshgrid(units, q, indexing="ij")
+    k0 = seed & 0xFFFFFFFF
+    k1 = ((seed >> 32) ^ (stream_id >> 32)) & 0xFFFFFFFF
+    x, y, z, w = philox4x32_10(Q, U & _MASK32, U >> np.uint64(32), np.full_like(Q, stream_id & 0xFFFFFFFF), k0, k1)
+    z0, z1 = _box_muller(x, y)
+    z2, z3 = _box_muller(z, w)
+    out = np.stack([z0, z1, z2, z3], axis=-1).reshape(len(units), nq * 4)
+    return out[:, :D]
+
+
+def philox_population(mu, sigma, n_rows: int, symmetric: bool, seed: int, stream_id: int, row0: int = 0) -> np.ndarray:
+    """Population rows [row0, row0 + n_rows) written by evok_sample_eval (float64 math, rounded to fp32)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    D = len(mu)
+    if symmetric:
+        units = np.arange(row0 // 2, (row0 + n_rows) // 2)
+        Z = philox_normals(seed, stream_id, units, D)
+        X = np.empty((n_rows, D))
+        X[0::2] = mu + sigma * Z
+        X[1::2] = mu - sigma * Z
+    else:
+        Z = philox_normals(seed, stream_id, np.arange(row0, row0 + n_rows), D)
+        X = mu + sigma * Z
+    return X.astype(F32)

@@ -1,0 +1,504 @@
+"""Parity of the sm_100a kernels (called through the C ABI of libevok.so via evotorch_b200.ops) against the numpy oracle
+and the golden vectors produced by the real reference.  Needs a CUDA device: run with `-m gpu` on the B200 box."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import es_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from evotorch_b200 import Problem, SolutionBatch, ops
+    from evotorch_b200 import _native as nat
+    from evotorch_b200.algorithms import CEM, PGPE, SNES
+    from evotorch_b200.distributions import ExpSeparableGaussian, SeparableGaussian, SymmetricSeparableGaussian
+    from evotorch_b200.objectives import ackley, rastrigin, sphere
+    from evotorch_b200.optimizers import SGD, Adam, ClipUp
+    from evotorch_b200.tools import modify_tensor, rank
+
+DEV = "cuda"
+METHODS = ("centered", "linear", "nes", "normalized", "raw")
+
+
+def C(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def test_library_is_loaded_and_is_the_in_tree_one():
+    lib = nat.lib()
+    assert lib.evok_abi_version() == 1
+    assert nat.LIB_PATH.endswith("evotorch_b200/lib/libevok.so")
+
+
+# ---------------------------------------------------------------------------------------------- K1 sampling
+@pytest.mark.parametrize("symmetric", [True, False])
+@pytest.mark.parametrize("n,D", [(64, 16), (10, 7), (6, 1), (48, 130), (2, 1000)])
+def test_sampler_matches_philox_restatement(symmetric, n, D):
+    rng = np.random.default_rng(D)
+    mu = rng.standard_normal(D).astype(np.float32)
+    sg = (np.abs(rng.standard_normal(D)) + 0.1).astype(np.float32)
+    X = torch.empty(n, D, device=DEV)
+    seed, sid = 0x1234_5678_9ABC_DEF0, 7
+    ops.sample_eval(ops.OBJ_NONE, X, C(mu), C(sg), n_rows=n, symmetric=symmetric, seed=seed, stream_id=sid)
+    ref = O.philox_population(mu, sg, n, symmetric, seed, sid)
+    close(N(X), ref, rtol=0, atol=3e-5 * float(sg.max()) + 1e-6)
+    if symmetric:
+        close(N(X[0::2] + X[1::2]), np.broadcast_to(2 * mu, (n // 2, D)), rtol=0, atol=1e-5)
+    # deterministic, and a different stream id gives a different population
+    X2 = torch.empty_like(X)
+    ops.sample_eval(ops.OBJ_NONE, X2, C(mu), C(sg), n_rows=n, symmetric=symmetric, seed=seed, stream_id=sid)
+    assert torch.equal(X, X2)
+    ops.sample_eval(ops.OBJ_NONE, X2, C(mu), C(sg), n_rows=n, symmetric=symmetric, seed=seed, stream_id=sid + 1)
+    assert not torch.equal(X, X2)
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_sampler_is_shard_and_geometry_independent(symmetric):
+    n, D = 4096, 256
+    mu = torch.linspace(-1, 1, D, device=DEV)
+    sg = torch.full((D,), 0.5, device=DEV)
+    whole = torch.empty(n, D, device=DEV)
+    ops.sample_eval(ops.OBJ_NONE, whole, mu, sg, n_rows=n, symmetric=symmetric, seed=42, stream_id=3)
+    for parts in ([1000, 3096], [512] * 8, [2, 4094]):
+        row0, pieces = 0, []
+        for m in parts:
+            x = torch.empty(m, D, device=DEV)
+            ops.sample_eval(ops.OBJ_NONE, x, mu, sg, n_rows=m, symmetric=symmetric, seed=42, stream_id=3, row0=row0)
+            pieces.append(x)
+            row0 += m
+        assert torch.equal(torch.cat(pieces), whole)
+    # a padded leading dimension (ldx > D) writes the same values
+    wide = torch.zeros(n, D + 4, device=DEV)
+    view = wide[:, :D]
+    ops.sample_eval(ops.OBJ_NONE, view, mu, sg, n_rows=n, symmetric=symmetric, seed=42, stream_id=3)
+    assert torch.equal(view, whole) and float(wide[:, D:].abs().max()) == 0.0
+
+
+def test_sampler_statistics_and_argument_errors():
+    n, D = 20000, 512
+    mu = torch.zeros(D, device=DEV)
+    sg = torch.ones(D, device=DEV)
+    X = torch.empty(n, D, device=DEV)
+    ops.sample_eval(ops.OBJ_NONE, X, mu, sg, n_rows=n, symmetric=False, seed=9, stream_id=0)
+    z = X.double()
+    assert abs(float(z.mean())) < 2e-3 and abs(float(z.std()) - 1) < 2e-3
+    assert abs(float((z**3).mean())) < 1e-2 and abs(float((z**4).mean()) - 3) < 3e-2
+    assert float(z.abs().max()) > 4.5  # tails are populated
+    # column and row correlations vanish
+    assert abs(float((z[:, 0] * z[:, 1]).mean())) < 0.03 and abs(float((z[0] * z[1]).mean())) < 0.2
+    # Kolmogorov-Smirnov distance of a 1e6-sample against the normal CDF
+    s = torch.sort(z.reshape(-1)[:1_000_000]).values
+    cdf = 0.5 * (1 + torch.erf(s / math.sqrt(2)))
+    ks = float((cdf - torch.arange(1, len(s) + 1, device=DEV, dtype=torch.float64) / len(s)).abs().max())
+    assert ks < 2.5e-3
+    with pytest.raises(ValueError):
+        ops.sample_eval(ops.OBJ_NONE, torch.empty(5, D, device=DEV), mu, sg, n_rows=5, symmetric=True, seed=0, stream_id=0)
+    with pytest.raises(ValueError):
+        ops.sample_eval(ops.OBJ_NONE, torch.empty(4, D, device=DEV), mu, sg, n_rows=4, symmetric=True, seed=0, stream_id=0, row0=1)
+    with pytest.raises(ValueError):
+        ops.sample_eval(ops.OBJ_RASTRIGIN, None, mu, sg, n_rows=4, symmetric=True, seed=0, stream_id=0)  # f missing
+    ops.sample_eval(ops.OBJ_NONE, torch.empty(0, D, device=DEV), mu, sg, n_rows=0, symmetric=True, seed=0, stream_id=0)  # empty is fine
+
+
+# ---------------------------------------------------------------------------------------------- K2 evaluation
+@pytest.mark.parametrize("objective", ["sphere", "rastrigin", "ackley"])
+@pytest.mark.parametrize("n,D", [(64, 16), (33, 7), (5, 1), (17, 1003), (8, 10000)])
+def test_eval_kernel_matches_oracle(objective, n, D):
+    rng = np.random.default_rng(n * D)
+    X = (rng.standard_normal((n, D)) * 2.5).astype(np.float32)
+    X64 = X.astype(np.float64)
+    if objective == "sphere":
+        ref = (X64**2).sum(1)
+    elif objective == "rastrigin":
+        ref = O.rastrigin(X).astype(np.float64)
+    else:
+        ref = -20 * np.exp(-0.2 * np.sqrt((X64**2).mean(1))) - np.exp(np.cos(2 * np.pi * X64).mean(1)) + 20 + np.e
+    got = N(ops.evaluate(ops.OBJECTIVE_IDS[objective], C(X)))
+    # fp32 accumulation of D terms + fast cos: relative 1e-6 * sqrt(D) of the value scale
+    close(got, ref, rtol=2e-6 * math.sqrt(D) + 2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+@pytest.mark.parametrize("objective", ["sphere", "rastrigin", "ackley"])
+def test_fused_sample_eval_is_consistent(symmetric, objective):
+    n, D = 512, 1000
+    oid = ops.OBJECTIVE_IDS[objective]
+    rng = np.random.default_rng(5)
+    mu = C(rng.uniform(-5.12, 5.12, D))
+    sg = C(np.full(D, 1.0))
+    X = torch.empty(n, D, device=DEV)
+    f = torch.empty(n, device=DEV)
+    ops.sample_eval(oid, X, mu, sg, n_rows=n, symmetric=symmetric, seed=77, stream_id=1, f=f)
+    Xs = torch.empty_like(X)
+    ops.sample_eval(ops.OBJ_NONE, Xs, mu, sg, n_rows=n, symmetric=symmetric, seed=77, stream_id=1)
+    assert torch.equal(X, Xs)  # fusing the evaluation does not change the population
+    f_lazy = torch.empty(n, device=DEV)
+    ops.sample_eval(oid, None, mu, sg, n_rows=n, symmetric=symmetric, seed=77, stream_id=1, f=f_lazy)
+    assert torch.equal(f, f_lazy)  # "lazy population": same fitness bits without materialising X
+    X64 = N(X).astype(np.float64)
+    if objective == "sphere":
+        ref = (X64**2).sum(1)
+    elif objective == "rastrigin":
+        ref = 10.0 * D + (X64**2 - 10 * np.cos(2 * np.pi * X64)).sum(1)
+    else:
+        ref = -20 * np.exp(-0.2 * np.sqrt((X64**2).mean(1))) - np.exp(np.cos(2 * np.pi * X64).mean(1)) + 20 + np.e
+    close(N(f), ref, rtol=1e-4, atol=1e-4)
+    close(N(ops.evaluate(oid, X)), ref, rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- K3 ranking
+@pytest.mark.parametrize("name", ["appxB", "reftest0", "reftest1", "rand257", "rand1000", "n2", "tied600"])
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("hib", [True, False])
+def test_rank_matches_reference_golden(golden, name, method, hib):
+    f = golden[f"rank/{name}/f"]
+    ref = golden[f"rank/{name}/{method}/{int(hib)}"]
+    perm = torch.empty(len(f), dtype=torch.int64, device=DEV)
+    got = N(ops.rank(C(f), method, hib, perm=perm))
+    if method in ("centered", "linear", "raw"):
+        np.testing.assert_array_equal(got, ref)  # bit exact against the reference's own output
+    else:
+        close(got, ref, rtol=3e-6, atol=3e-7)
+    np.testing.assert_array_equal(N(perm), O.argsort_for_ranking(f, hib))  # bit-exact ranking indices
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 2048, 2049, 100_003, 1_000_000])
+@pytest.mark.parametrize("hib", [True, False])
+def test_rank_large_with_ties_nan_and_signed_zero(n, hib):
+    rng = np.random.default_rng(n)
+    f = (rng.standard_normal(n) * 717 + 1.1e5).astype(np.float32)  # fp32 Rastrigin-like: massive collisions at large n
+    if n > 100:
+        f[::97] = 0.0
+        f[1::97] = -0.0
+        f[5::1013] = np.nan
+        f[7::5003] = np.inf
+        f[11::5003] = -np.inf
+    perm = torch.empty(n, dtype=torch.int64, device=DEV)
+    w = N(ops.rank(C(f), "centered", hib, perm=perm))
+    order = O.argsort_for_ranking(f, hib)
+    np.testing.assert_array_equal(N(perm), order)
+    if n > 1:
+        np.testing.assert_array_equal(w, O.rank_centered(f, hib))
+    np.testing.assert_array_equal(N(ops.argsort(C(f), descending=not hib)), order)
+    if n >= 31:
+        close(N(ops.rank(C(f[np.isfinite(f)]), "nes", hib)), O.rank_nes(f[np.isfinite(f)], hib), rtol=2e-5, atol=2e-9)
+
+
+def test_rank_properties_and_helpers():
+    n = 300_000
+    f = torch.randn(n, device=DEV) * 3
+    w = ops.rank(f, "centered", False)
+    # utilities are a permutation of the table, and monotone in fitness (lower f -> higher utility for "min")
+    sw = torch.sort(w).values
+    table = torch.arange(n, device=DEV, dtype=torch.float32) / (n - 1) - 0.5
+    assert torch.equal(sw, table)
+    order = torch.argsort(f, stable=True)
+    assert bool((w[order][:-1] >= w[order][1:]).all())
+    # weight adjustments
+    w2 = ops.weights_adjust_(ops.rank(f, "nes", False).clone(), 1)
+    assert abs(float(w2.double().sum())) < 1e-4
+    w3 = ops.weights_adjust_(ops.rank(f, "linear", False).clone(), 2)
+    assert abs(float(w3.abs().double().sum()) - 1) < 1e-5
+    # elite mask = the k largest weights, ties by ascending index
+    wt = torch.tensor([1.0, 5.0, 5.0, 2.0, 5.0, 0.0], device=DEV)
+    assert ops.elite_mask(wt, 2).tolist() == [0, 1, 1, 0, 0, 0]
+    assert ops.elite_mask(wt, 4).tolist() == [0, 1, 1, 1, 1, 0]
+    with pytest.raises(KeyError):
+        ops.rank(f, "nope", True)
+
+
+# ---------------------------------------------------------------------------------------------- K4 gradients
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("sense", ["min", "max"])
+def test_gradients_match_reference_golden(golden, method, sense):
+    mu, sg = C(golden["grad/mu"]), C(golden["grad/sigma"])
+    for div in ("num_directions", "num_solutions", "total_weight", "weight_stdev", None):
+        extra = {} if div is None else {"divide_mu_grad_by": div, "divide_sigma_grad_by": div}
+        d = SymmetricSeparableGaussian({"mu": mu, "sigma": sg, **extra})
+        g = d.compute_gradients(C(golden["grad/Xsym"]), C(golden["grad/fsym"]), objective_sense=sense, ranking_method=method)
+        scale = max(1.0, float(np.abs(golden[f"grad/sym/{method}/{sense}/{div}/sigma"]).max()))
+        close(N(g["mu"]), golden[f"grad/sym/{method}/{sense}/{div}/mu"], rtol=2e-4, atol=2e-5 * scale)
+        close(N(g["sigma"]), golden[f"grad/sym/{method}/{sense}/{div}/sigma"], rtol=2e-4, atol=2e-5 * scale)
+        d = SeparableGaussian({"mu": mu, "sigma": sg, **extra})
+        g = d.compute_gradients(C(golden["grad/Xns"]), C(golden["grad/fns"]), objective_sense=sense, ranking_method=method)
+        scale = max(1.0, float(np.abs(golden[f"grad/sep/{method}/{sense}/{div}/sigma"]).max()))
+        close(N(g["mu"]), golden[f"grad/sep/{method}/{sense}/{div}/mu"], rtol=2e-4, atol=2e-5 * scale)
+        close(N(g["sigma"]), golden[f"grad/sep/{method}/{sense}/{div}/sigma"], rtol=2e-4, atol=2e-5 * scale)
+    d = ExpSeparableGaussian({"mu": mu, "sigma": sg})
+    g = d.compute_gradients(C(golden["grad/Xns"]), C(golden["grad/fns"]), objective_sense=sense, ranking_method=method)
+    close(N(g["mu"]), golden[f"grad/exp/{method}/{sense}/mu"], rtol=2e-4, atol=2e-5)
+    close(N(g["sigma"]), golden[f"grad/exp/{method}/{sense}/sigma"], rtol=2e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("ratio", [0.5, 0.25, 0.1])
+@pytest.mark.parametrize("sense", ["min", "max"])
+def test_cem_gradients_match_reference_golden(golden, ratio, sense):
+    d = SeparableGaussian({"mu": C(golden["grad/mu"]), "sigma": C(golden["grad/sigma"]), "parenthood_ratio": ratio})
+    g = d.compute_gradients(C(golden["grad/Xns"]), C(golden["grad/fns"]), objective_sense=sense, ranking_method=None)
+    close(N(g["mu"]), golden[f"grad/cem/{ratio}/{sense}/mu"], rtol=2e-5, atol=3e-6)
+    close(N(g["sigma"]), golden[f"grad/cem/{ratio}/{sense}/sigma"], rtol=2e-5, atol=3e-6)
+
+
+@pytest.mark.parametrize("form", ["separable", "symmetric", "exp", "moments"])
+@pytest.mark.parametrize("n,D", [(2, 1), (6, 3), (64, 16), (130, 7), (1000, 130), (514, 1000), (4096, 1030), (256, 10000), (20000, 64)])
+def test_grad_kernel_matches_oracle_ragged_shapes(form, n, D):
+    rng = np.random.default_rng(n + D)
+    mu = rng.standard_normal(D).astype(np.float32)
+    sg = (np.abs(rng.standard_normal(D)) * 0.5 + 0.2).astype(np.float32)
+    X = (mu + sg * rng.standard_normal((n, D))).astype(np.float32)
+    w = (rng.standard_normal(n) / n).astype(np.float32)
+    if form == "moments":
+        w = (rng.random(n) < 0.3).astype(np.float32)
+    fid = {"separable": ops.GRAD_SEPARABLE, "symmetric": ops.GRAD_SYMMETRIC, "exp": ops.GRAD_EXP, "moments": ops.GRAD_MOMENTS}[form]
+    gm, gs = ops.grad(fid, C(X), C(w), C(mu), C(sg), 0.5, 2.0)
+    w64, X64, mu64, sg64 = w.astype(np.float64), X.astype(np.float64), mu.astype(np.float64), sg.astype(np.float64)
+    if form == "symmetric":
+        eps = X64[0::2] - mu64
+        a, b = (w64[0::2] - w64[1::2]) / 2, (w64[0::2] + w64[1::2]) / 2
+        g = (eps**2 - sg64**2) / sg64
+    else:
+        eps = X64 - mu64
+        a = b = w64
+        g = {"separable": (eps**2 - sg64**2) / sg64, "exp": (eps / sg64) ** 2 - 1, "moments": eps**2}[form]
+    ref_m = 0.5 * (a[:, None] * eps).sum(0)
+    ref_s = 2.0 * (b[:, None] * g).sum(0)
+    tol_m = 3e-6 * 0.5 * (np.abs(a)[:, None] * np.abs(eps)).sum(0).max() + 1e-9
+    tol_s = 3e-6 * 2.0 * (np.abs(b)[:, None] * (np.abs(g) + 1)).sum(0).max() + 1e-9
+    close(N(gm), ref_m, rtol=1e-4, atol=tol_m)
+    close(N(gs), ref_s, rtol=1e-4, atol=tol_s)
+    # a strided (padded) population gives identical bits
+    wide = torch.zeros(n, D + 3, device=DEV)
+    wide[:, :D] = C(X)
+    gm2, gs2 = ops.grad(fid, wide[:, :D], C(w), C(mu), C(sg), 0.5, 2.0)
+    close(N(gm2), N(gm), rtol=1e-5, atol=tol_m)
+    close(N(gs2), N(gs), rtol=1e-5, atol=tol_s)
+
+
+def test_grad_is_deterministic_linear_and_shard_additive():
+    n, D = 8192, 2000
+    g = torch.Generator(device=DEV).manual_seed(1)
+    mu = torch.randn(D, device=DEV, generator=g)
+    sg = torch.rand(D, device=DEV, generator=g) + 0.5
+    X = mu + sg * torch.randn(n, D, device=DEV, generator=g)
+    w1 = torch.randn(n, device=DEV, generator=g) / n
+    w2 = torch.randn(n, device=DEV, generator=g) / n
+    a1 = ops.grad(ops.GRAD_SYMMETRIC, X, w1, mu, sg, 1.0, 1.0)
+    a1b = ops.grad(ops.GRAD_SYMMETRIC, X, w1, mu, sg, 1.0, 1.0)
+    assert torch.equal(a1[0], a1b[0]) and torch.equal(a1[1], a1b[1])  # no atomics: bit-reproducible
+    a2 = ops.grad(ops.GRAD_SYMMETRIC, X, w2, mu, sg, 1.0, 1.0)
+    a12 = ops.grad(ops.GRAD_SYMMETRIC, X, w1 + w2, mu, sg, 1.0, 1.0)
+    for k in range(2):
+        close(N(a12[k]), N(a1[k] + a2[k]), rtol=1e-4, atol=2e-6)
+    parts = [(0, 1000), (1000, 5000), (5000, 8192)]
+    acc = [torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)]
+    for lo, hi in parts:
+        p = ops.grad(ops.GRAD_SYMMETRIC, X[lo:hi], w1[lo:hi], mu, sg, 1.0, 1.0)
+        acc[0] += p[0]
+        acc[1] += p[1]
+    for k in range(2):
+        close(N(acc[k]), N(a1[k]), rtol=1e-4, atol=2e-6)
+    # rows whose weights are zero are skipped without changing the result
+    wz = w1.clone()
+    wz[2000:6000] = 0
+    z = ops.grad(ops.GRAD_SEPARABLE, X, wz, mu, sg, 1.0, 1.0)
+    zz = ops.grad(ops.GRAD_SEPARABLE, torch.cat([X[:2000], X[6000:]]), torch.cat([wz[:2000], wz[6000:]]), mu, sg, 1.0, 1.0)
+    for k in range(2):
+        close(N(z[k]), N(zz[k]), rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_grad_regen_equals_materialised_path(symmetric):
+    n, D = 2048, 1000
+    mu = torch.linspace(-2, 2, D, device=DEV)
+    sg = torch.rand(D, device=DEV) + 0.3
+    X = torch.empty(n, D, device=DEV)
+    row0 = 512
+    ops.sample_eval(ops.OBJ_NONE, X, mu, sg, n_rows=n, symmetric=symmetric, seed=5, stream_id=9, row0=row0)
+    w = torch.randn(n, device=DEV) / n
+    form = ops.GRAD_SYMMETRIC if symmetric else ops.GRAD_SEPARABLE
+    a = ops.grad(form, X, w, mu, sg, 1.0, 1.0)
+    b = ops.grad_regen(form, w, mu, sg, seed=5, stream_id=9, row0=row0, scale_mu=1.0, scale_sigma=1.0)
+    for k in range(2):
+        close(N(b[k]), N(a[k]), rtol=2e-4, atol=3e-6)
+
+
+# ---------------------------------------------------------------------------------------------- K5 updates
+def test_optimizer_kernels_match_reference_golden(golden):
+    grads = golden["opt/grads"]
+    for i in range(4):
+        ss, mom, ms = golden[f"opt/clipup/{i}/cfg"]
+        opt = ClipUp(solution_length=12, dtype="float32", stepsize=ss, momentum=mom, max_speed=None if ms < 0 else ms, device=DEV)
+        got = np.stack([N(opt.ascent(C(g))) for g in grads])
+        close(got, golden[f"opt/clipup/{i}/steps"], rtol=3e-6, atol=3e-7)
+        # fused mu += step gives the same trajectory
+        opt2 = ClipUp(solution_length=12, dtype="float32", stepsize=ss, momentum=mom, max_speed=None if ms < 0 else ms, device=DEV)
+        m = torch.zeros(12, device=DEV)
+        for g in grads:
+            opt2.ascent_into_(C(g), m)
+        close(N(m), golden[f"opt/clipup/{i}/steps"].sum(0), rtol=1e-5, atol=1e-6)
+    for tag, kw in (("adam/0", dict(stepsize=0.05)), ("adam/1", dict(stepsize=0.01, beta1=0.8, beta2=0.95, epsilon=1e-6))):
+        opt = Adam(solution_length=12, dtype="float32", device=DEV, **kw)
+        close(np.stack([N(opt.ascent(C(g))) for g in grads]), golden[f"opt/{tag}/steps"], rtol=1e-5, atol=1e-7)
+    for tag, kw in (("sgd/0", dict(stepsize=0.1)), ("sgd/1", dict(stepsize=0.1, momentum=0.8))):
+        opt = SGD(solution_length=12, dtype="float32", device=DEV, **kw)
+        close(np.stack([N(opt.ascent(C(g))) for g in grads]), golden[f"opt/{tag}/steps"], rtol=3e-6, atol=1e-7)
+    # a large vector exercises the multi-iteration single-CTA reductions
+    D = 100_003
+    g = torch.randn(D, device=DEV)
+    opt = ClipUp(solution_length=D, dtype="float32", stepsize=0.5, device=DEV)
+    ref = O.ClipUp(D, 0.5)
+    for _ in range(4):
+        close(N(opt.ascent(g)), ref.ascent(N(g)), rtol=1e-5, atol=1e-8)
+
+
+def test_sigma_update_kernel_matches_modify_tensor(golden):
+    xo, xt = golden["modify/r/orig"], golden["modify/r/target"]
+    s = C(np.abs(xo) + 0.1)
+    g = C(xt)
+    for exp_form in (False, True):
+        for kw in ({}, {"max_change": 0.2}, {"lb": 0.05, "ub": 1.0, "max_change": 0.5}, {"lb": C(np.full(16, 0.3))},
+                   {"ub": C(np.linspace(0.2, 2.0, 16))}, {"max_change": C(np.linspace(0.01, 0.9, 16))}):
+            cur = s.clone()
+            ops.sigma_update_(cur, g, 0.3, exp_form, **kw)
+            target = s * torch.exp(0.5 * 0.3 * g) if exp_form else s + 0.3 * g
+            ref = modify_tensor(s, target, **kw)
+            close(N(cur), N(ref), rtol=2e-6, atol=1e-7)
+    # the reference's own known answers
+    x = C([10, 11, 12])
+    for kw, ans in (({"lb": 5}, [5, 21, 22]), ({"lb": 5, "ub": 20}, [5, 20, 20]), ({"max_change": 0.5}, [5, 16.5, 18]),
+                    ({"lb": 7, "ub": 17, "max_change": 0.5}, [7, 16.5, 17])):
+        cur = x.clone()
+        ops.sigma_update_(cur, C([-10, 10, 10]), 1.0, False, **kw)
+        assert cur.tolist() == ans
+
+
+# ---------------------------------------------------------------------------------------------- whole generations
+TRAJ = {
+    "pgpe": lambda p, mu, sg: PGPE(p, popsize=32, center_learning_rate=0.5, stdev_learning_rate=0.1, center_init=mu, stdev_init=sg),
+    "pgpe_max": lambda p, mu, sg: PGPE(p, popsize=32, center_learning_rate=0.5, stdev_learning_rate=0.1, center_init=mu, stdev_init=sg),
+    "pgpe_nonsym_adam": lambda p, mu, sg: PGPE(p, popsize=30, center_learning_rate=0.05, stdev_learning_rate=0.1, center_init=mu,
+                                                stdev_init=sg, symmetric=False, optimizer="adam"),
+    "pgpe_nes_rank": lambda p, mu, sg: PGPE(p, popsize=32, center_learning_rate=0.3, stdev_learning_rate=0.1, center_init=mu,
+                                             stdev_init=sg, ranking_method="nes", optimizer=None, stdev_min=0.01, stdev_max=2.0),
+    "snes": lambda p, mu, sg: SNES(p, popsize=24, center_init=mu, stdev_init=sg),
+    "snes_clipup": lambda p, mu, sg: SNES(p, popsize=24, center_init=mu, stdev_init=sg, optimizer="clipup", center_learning_rate=0.2,
+                                           stdev_max_change=0.3),
+    "cem": lambda p, mu, sg: CEM(p, popsize=40, parenthood_ratio=0.25, center_init=mu, stdev_init=sg, stdev_max_change=0.5),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(TRAJ))
+def test_seeded_reference_trajectory_through_the_cuda_searcher(golden, tag):
+    """Feed the reference's recorded populations (X_t, f_t) to the CUDA searcher generation by generation: its
+    rank -> gradient -> update kernels must reproduce the reference's (mu_{t+1}, sigma_{t+1}) within 1e-5 relative."""
+    mu, sg, X, f = (golden[f"traj/{tag}/{k}"] for k in ("mu", "sigma", "X", "f"))
+    T, n, D = X.shape
+    sense = "max" if tag == "pgpe_max" else "min"
+    prob = Problem(sense, rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=DEV, seed=11)
+    s = TRAJ[tag](prob, C(mu[0]), C(sg[0]))
+    s.step()  # generation 1: sample + evaluate only (with our own Philox population, replaced below)
+    for t in range(T - 1):
+        s._population.set_values(C(X[t]))
+        s._population.set_evals(C(f[t]))
+        s.step()
+        close(N(s.status["center"]), mu[t + 1], rtol=1e-5, atol=2e-6)
+        close(N(s.status["stdev"]), sg[t + 1], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("algo", ["pgpe", "pgpe_nonsym", "snes", "cem"])
+def test_cuda_searchers_optimise_and_are_seed_deterministic(algo):
+    def make(seed):
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=200, device=DEV, seed=seed)
+        if algo == "pgpe":
+            return PGPE(prob, popsize=2000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+        if algo == "pgpe_nonsym":
+            return PGPE(prob, popsize=2000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0, symmetric=False)
+        if algo == "snes":
+            return SNES(prob, popsize=2000, stdev_init=3.0)
+        return CEM(prob, popsize=2000, parenthood_ratio=0.2, stdev_init=3.0)
+
+    a, b, c = make(4), make(4), make(5)
+    a.step()
+    first = a.status["mean_eval"]
+    a.run(60)
+    b.run(61)
+    c.run(61)
+    assert a.status["mean_eval"] < 0.7 * first
+    assert torch.equal(a.status["center"], b.status["center"]) and torch.equal(a.status["stdev"], b.status["stdev"])
+    assert not torch.equal(a.status["center"], c.status["center"])
+    assert a.population.values.is_cuda and a.population.evals.shape == (2000, 1)
+    assert math.isfinite(a.status["pop_best_eval"]) and a.status["pop_best"].values.shape == (200,)
+
+
+def test_user_objective_and_torch_rng_paths_on_cuda():
+    def my_sphere(x):
+        return torch.sum(x * x, dim=-1)
+
+    prob = Problem("min", my_sphere, initial_bounds=(-3, 3), solution_length=64, device=DEV, seed=1, vectorized=True)
+    s = PGPE(prob, popsize=500, center_learning_rate=0.3, stdev_learning_rate=0.1, stdev_init=1.0)
+    s.step()
+    m0 = s.status["mean_eval"]
+    s.run(40)
+    assert s.status["mean_eval"] < 0.5 * m0
+    prob_t = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=64, device=DEV, seed=1, rng="torch")
+    st = PGPE(prob_t, popsize=500, center_learning_rate=0.3, stdev_learning_rate=0.1, stdev_init=1.0)
+    st.run(3)
+    X = st.population.values
+    close(N(X[0::2] + X[1::2]), np.broadcast_to(2 * N(st.status["center"]), (250, 64)), rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_config2_size_properties():
+    """BASELINE configs[1]: PGPE, Rastrigin, N = 100 000, D = 10 000 (4 GB population) -- size-independent properties."""
+    n, D = 100_000, 10_000
+    prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=DEV, seed=0)
+    s = PGPE(prob, popsize=n, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+    s.step()
+    X, f = s.population.values, s.population.evals[:, 0]
+    mu, sg = s.status["center"], s.status["stdev"]
+    # antithetic pairs mirror around mu (1 ulp of |x|)
+    rows = torch.randint(0, n // 2, (64,), device=DEV)
+    assert float((X[2 * rows] + X[2 * rows + 1] - 2 * mu).abs().max()) < 4e-6
+    # fused fitness == stand-alone evaluation of the stored population
+    f2 = ops.evaluate(ops.OBJ_RASTRIGIN, X)
+    assert float(((f - f2).abs() / f2).max()) < 2e-6
+    sub = torch.randint(0, n, (16,), device=DEV)
+    close(N(f[sub]), O.rastrigin(N(X[sub])), rtol=3e-6)
+    # sample moments of the perturbations
+    z = ((X[0::2][:2000] - mu) / sg).double()
+    assert abs(float(z.mean())) < 1e-3 and abs(float(z.std()) - 1) < 1e-3
+    # ranks are a permutation of the utility table and sorted consistently with the fitnesses
+    w = rank(f, "centered", higher_is_better=False)
+    assert torch.equal(torch.sort(w).values, torch.arange(n, device=DEV, dtype=torch.float32) / (n - 1) - 0.5)
+    order = ops.argsort(f, descending=True)
+    assert bool((f[order][:-1] >= f[order][1:]).all()) and bool((w[order][:-1] <= w[order][1:]).all())
+    # gradient of the whole population == sum over 3 uneven shards; regenerated-from-Philox gradient agrees
+    d = s._distribution
+    whole = d._compute_gradients(X, w, "centered")
+    acc = {k: torch.zeros(D, device=DEV) for k in ("mu", "sigma")}
+    for lo, hi in ((0, 30_000), (30_000, 30_002), (30_002, n)):
+        p = d.partial_gradients(X[lo:hi], w, lo, "centered")
+        for k in acc:
+            acc[k] += p[k]
+    for k in acc:
+        close(N(acc[k]), N(whole[k]), rtol=1e-3, atol=2e-7)
+    regen = ops.grad_regen(ops.GRAD_SYMMETRIC, w, mu, sg, seed=prob._philox_seed, stream_id=prob._philox_stream - 1, row0=0,
+                           scale_mu=1.0 / (n // 2), scale_sigma=1.0 / (n // 2))
+    close(N(regen[0]), N(whole["mu"]), rtol=1e-3, atol=3e-7)
+    close(N(regen[1]), N(whole["sigma"]), rtol=1e-3, atol=3e-7)
+    # and a few generations make progress
+    m0 = s.status["mean_eval"]
+    s.run(5)
+    assert s.status["mean_eval"] < m0
