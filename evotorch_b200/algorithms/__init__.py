@@ -1,5 +1,6 @@
+from .cmaes import CMAES
 from .gaussian import CEM, PGPE, SNES, XNES, GaussianSearchAlgorithm
 from .searchalgorithm import LazyReporter, LazyStatusDict, SearchAlgorithm, SinglePopulationAlgorithmMixin
 
-__all__ = ["PGPE", "SNES", "CEM", "XNES", "GaussianSearchAlgorithm", "SearchAlgorithm", "LazyReporter", "LazyStatusDict",
+__all__ = ["CMAES", "PGPE", "SNES", "CEM", "XNES", "GaussianSearchAlgorithm", "SearchAlgorithm", "LazyReporter", "LazyStatusDict",
            "SinglePopulationAlgorithmMixin"]

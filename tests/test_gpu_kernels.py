@@ -459,6 +459,41 @@ def test_user_objective_and_torch_rng_paths_on_cuda():
     close(N(X[0::2] + X[1::2]), np.broadcast_to(2 * N(st.status["center"]), (250, 64)), rtol=0, atol=1e-5)
 
 
+def test_cmaes_on_cuda_reproduces_reference_trajectory(golden):
+    """The reference's CMA-ES run (its z draws recorded) through the CUDA searcher: GEMM sampling, K2 evaluation, K3 ranking,
+    K4 weighted recombination, rank-mu SYRK and Cholesky must reproduce (m, sigma, C, A, paths)."""
+    from evotorch_b200.algorithms import CMAES
+
+    Z = golden["cmaes/Z"]
+    T, n, D = Z.shape
+    prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=D, device=DEV, seed=3)
+    c = CMAES(prob, stdev_init=1.0, popsize=n, center_init=C(golden["cmaes/m0"]))
+    close(N(c.weights), golden["cmaes/weights"], rtol=2e-6, atol=1e-8)
+    for t in range(T):
+        zt = C(Z[t])
+
+        def recorded_sample(num_samples=None, zt=zt):
+            ys = zt @ c.A.T
+            return zt, ys, c.m.unsqueeze(0) + c.sigma * ys
+
+        c.sample_distribution = recorded_sample
+        c.step()
+        close(N(c.population.evals[:, 0]), golden["cmaes/f"][t], rtol=2e-5, atol=1e-5)
+        close(N(c.m), golden["cmaes/m"][t], rtol=2e-5, atol=3e-6)
+        close(float(c.sigma), golden["cmaes/sigma"][t][0], rtol=2e-5)
+        close(N(c.C), golden["cmaes/C"][t], rtol=2e-5, atol=3e-6)
+        close(N(c.A), golden["cmaes/A"][t], rtol=2e-5, atol=3e-6)
+        close(N(c.p_sigma), golden["cmaes/p_sigma"][t], rtol=2e-5, atol=3e-6)
+        close(N(c.p_c), golden["cmaes/p_c"][t], rtol=2e-5, atol=3e-6)
+    # with its own Philox draws it optimises
+    prob2 = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=64, device=DEV, seed=1)
+    c2 = CMAES(prob2, stdev_init=1.0, popsize=256)
+    c2.step()
+    m0 = c2.status["mean_eval"]
+    c2.run(60)
+    assert c2.status["mean_eval"] < 0.2 * m0
+
+
 # ---------------------------------------------------------------------------------------------- full-size properties
 def test_config2_size_properties():
     """BASELINE configs[1]: PGPE, Rastrigin, N = 100 000, D = 10 000 (4 GB population) -- size-independent properties."""

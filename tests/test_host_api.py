@@ -235,3 +235,31 @@ def test_stdout_logger(capsys):
     s.run(4)
     out = capsys.readouterr().out
     assert out.count("iter") == 2 and "mean_eval" in out
+
+
+def test_cmaes_cpu_trajectory_matches_reference(golden):
+    from evotorch_b200.algorithms import CMAES
+
+    prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=6, vectorized=True, seed=3, dtype=torch.float32)
+    c = CMAES(prob, stdev_init=1.0, popsize=12)
+    np.testing.assert_allclose(c.weights.numpy(), golden["cmaes/weights"], rtol=2e-6, atol=1e-8)
+    consts = golden["cmaes/consts"]
+    np.testing.assert_allclose([c.mu_eff, c.c_sigma, c.damp_sigma, c.c_c, c.c_1, c.c_mu, c.decompose_C_freq], consts, rtol=2e-6)
+    for t in range(6):
+        c.step()
+        np.testing.assert_allclose(c.m.numpy(), golden["cmaes/m"][t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(float(c.sigma), golden["cmaes/sigma"][t][0], rtol=1e-5)
+        np.testing.assert_allclose(c.C.numpy(), golden["cmaes/C"][t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(c.A.numpy(), golden["cmaes/A"][t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(c.p_sigma.numpy(), golden["cmaes/p_sigma"][t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(c.p_c.numpy(), golden["cmaes/p_c"][t], rtol=1e-5, atol=2e-6)
+    assert "stepsize" in c.status and "center" in c.status and c.status["iter"] == 6
+    big = CMAES(Problem("min", sphere, initial_bounds=(-3, 3), solution_length=1024, vectorized=True, seed=3), stdev_init=1.0, popsize=4096)
+    ref = golden["cmaes/cfg3_consts"]
+    np.testing.assert_allclose([big.mu_eff, big.c_sigma, big.damp_sigma, big.c_c, big.c_1, big.c_mu, big.decompose_C_freq,
+                                float(torch.sum(big.weights))], ref, rtol=5e-6)
+    sep = CMAES(Problem("min", sphere, initial_bounds=(-3, 3), solution_length=20, vectorized=True, seed=3), stdev_init=1.0, separable=True)
+    sep.step()
+    m0 = sep.status["mean_eval"]
+    sep.run(40)
+    assert sep.status["mean_eval"] < m0 and sep.C.ndim == 1
