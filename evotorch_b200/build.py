@@ -54,16 +54,20 @@ def is_up_to_date() -> bool:
     return os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and is_up_to_date():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: str = "") -> str:
+    """Build libevok.so.  `defines` / `tag` build a tuning variant lib/libevok_<tag>.so (used by scripts/kbench.py)."""
+    global OBJDIR
+    lib_path = LIB if not tag else os.path.join(LIBDIR, f"libevok_{tag}.so")
+    if not tag and not force and is_up_to_date():
         return LIB
     nvcc = _nvcc()
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = OBJDIR if not tag else os.path.join(PKG, "build", f"obj_{tag}")
+    os.makedirs(objdir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
@@ -74,14 +78,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB + ".tmp", *objs,
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", lib_path + ".tmp", *objs,
            "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(lib_path + ".tmp", lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":

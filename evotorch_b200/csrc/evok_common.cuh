@@ -30,20 +30,38 @@ struct U4 {
   uint32_t x, y, z, w;
 };
 
-__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// The 10 round keys of one (seed, stream) pair, precomputed on the host and passed to the kernels BY VALUE: they live in
+// the constant bank, so each round's key XOR takes its operand straight from c[][] (no per-thread key-schedule adds).
+struct PhiloxKey {
+  uint32_t k0[10], k1[10];
+  uint32_t stream_lo;
+};
+
+inline PhiloxKey make_philox_key(uint64_t seed, uint64_t stream_id) {
+  PhiloxKey k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.k0[r] = a;
+    k.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  k.stream_lo = (uint32_t)stream_id;
+  return k;
+}
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKey& key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     U4 n;
-    n.x = hi1 ^ c.y ^ k0;
+    n.x = hi1 ^ c.y ^ key.k0[r];
     n.y = lo1;
-    n.z = hi0 ^ c.w ^ k1;
+    n.z = hi0 ^ c.w ^ key.k1[r];
     n.w = lo0;
     c = n;
-    k0 += W0;
-    k1 += W1;
   }
   return c;
 }
@@ -75,13 +93,13 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 
 // The four standard normals of (unit, column group q): `unit` is the GLOBAL direction index (symmetric
 // sampling: rows 2*unit and 2*unit+1) or the global row index (non-symmetric); columns 4q .. 4q+3.
-__device__ __forceinline__ void normals4(uint64_t seed, uint64_t stream_id, uint64_t unit, uint32_t q, float z[4]) {
+__device__ __forceinline__ void normals4(const PhiloxKey& key, uint64_t unit, uint32_t q, float z[4]) {
   U4 c;
   c.x = q;
   c.y = (uint32_t)unit;
   c.z = (uint32_t)(unit >> 32);
-  c.w = (uint32_t)stream_id;
-  const U4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
+  c.w = key.stream_lo;
+  const U4 r = philox4x32_10(c, key);
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);
 }

@@ -4,12 +4,27 @@
 // HBM-bound: each CTA owns a column tile (128-bit loads, 4 rows in flight per thread) and a contiguous chunk of
 // rows; partial sums go to a [chunk][2][D] workspace and a second tiny kernel adds the chunks in a fixed order
 // (deterministic, no atomics).  In the symmetric form only the even ("+") rows are read.
+#include <cstdlib>
+
 #include "evok_common.cuh"
+
+#ifndef EVOK_GRAD_TMA_DEFAULT
+#define EVOK_GRAD_TMA_DEFAULT 1
+#endif
 
 namespace evok {
 
+#ifndef EVOK_GRAD_UNROLL
+#define EVOK_GRAD_UNROLL 4
+#endif
+#ifndef EVOK_GRAD_MINB
+#define EVOK_GRAD_MINB 4
+#endif
+#ifndef EVOK_GRAD_CTAS_PER_SM
+#define EVOK_GRAD_CTAS_PER_SM 4
+#endif
 constexpr int kGradThreads = 256;
-constexpr int kGradUnroll = 4;
+constexpr int kGradUnroll = EVOK_GRAD_UNROLL;
 constexpr int kMaxResidentCtas = 148 * 8;
 
 template <int VEC>
@@ -37,10 +52,10 @@ __device__ __forceinline__ VecF<VEC> load_row(const float* p) {
 
 // SYM: unit r = direction (rows 2r, 2r+1), else unit r = row r.  REGEN: eps = sigma * z regenerated from Philox.
 template <int VEC, int TX, bool SYM, bool REGEN>
-__global__ void __launch_bounds__(kGradThreads)
+__global__ void __launch_bounds__(kGradThreads, EVOK_GRAD_MINB)
     grad_partial_kernel(int form, const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, const float* __restrict__ mu,
-                        const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk, uint64_t unit0, uint64_t seed,
-                        uint64_t stream_id, float* __restrict__ partial) {
+                        const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk, uint64_t unit0,
+                        const __grid_constant__ PhiloxKey key, float* __restrict__ partial) {
   constexpr int TY = kGradThreads / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int64_t col = ((int64_t)blockIdx.x * TX + tx) * VEC;
@@ -97,10 +112,10 @@ __global__ void __launch_bounds__(kGradThreads)
       if (need[u]) {
         if (REGEN) {
           if (VEC == 4) {
-            normals4(seed, stream_id, unit0 + (uint64_t)r, (uint32_t)(col >> 2), x[u].v);
+            normals4(key, unit0 + (uint64_t)r, (uint32_t)(col >> 2), x[u].v);
           } else {
             float z[4];
-            normals4(seed, stream_id, unit0 + (uint64_t)r, (uint32_t)(col >> 2), z);
+            normals4(key, unit0 + (uint64_t)r, (uint32_t)(col >> 2), z);
             x[u].v[0] = z[col & 3];
           }
         } else {
@@ -169,6 +184,172 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restr
   out_sigma[j] = t2 * scale_sigma;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the partial kernel: a producer warp streams row segments global -> shared with 1-D bulk async
+// copies (cp.async.bulk, completion counted on an mbarrier), S stages of R rows x 4 KB deep, so each SM keeps
+// 2 CTAs x S x R x 4 KB in flight without spending registers or issue slots on loads; 8 consumer warps read the staged
+// rows from shared memory (128-bit, conflict free) and accumulate.  Column tile = 1024 columns, one float4 per thread.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef EVOK_GRAD_TMA_ROWS
+#define EVOK_GRAD_TMA_ROWS 4
+#endif
+#ifndef EVOK_GRAD_TMA_STAGES
+#define EVOK_GRAD_TMA_STAGES 4
+#endif
+#ifndef EVOK_GRAD_TMA_CTAS_PER_SM
+#define EVOK_GRAD_TMA_CTAS_PER_SM 3
+#endif
+constexpr int kTmaRows = EVOK_GRAD_TMA_ROWS;
+constexpr int kTmaStages = EVOK_GRAD_TMA_STAGES;
+constexpr int kTmaCols = 1024;
+constexpr int kTmaConsumers = 256;
+constexpr int kTmaThreads = kTmaConsumers + 32;
+constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * kTmaRows * kTmaCols * sizeof(float) + 2 * kTmaStages * sizeof(uint64_t) + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(kTmaThreads, EVOK_GRAD_TMA_CTAS_PER_SM)
+    grad_partial_tma_kernel(int form, const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, const float* __restrict__ mu,
+                            const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk,
+                            float* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTmaStages * kTmaRows * kTmaCols * sizeof(float));
+  uint64_t* empty = full + kTmaStages;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t col0 = (int64_t)blockIdx.x * kTmaCols;
+  const int64_t width = min((int64_t)kTmaCols, D - col0);  // columns of this tile (multiple of 4)
+  const int64_t r_begin = (int64_t)blockIdx.y * units_per_chunk;
+  const int64_t r_end = min(n_units, r_begin + units_per_chunk);
+  const int64_t n_rows = r_end - r_begin;
+  const int64_t n_groups = (n_rows + kTmaRows - 1) / kTmaRows;
+  const int64_t row_stride = (SYM ? 2 : 1) * ldx;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumers / 32) {
+    // ===== producer warp: one elected lane issues the bulk copies =====
+    if (lane == 0) {
+      const uint32_t row_bytes = (uint32_t)(width * sizeof(float));
+      for (int64_t g = 0; g < n_groups; ++g) {
+        const int s = (int)(g % kTmaStages);
+        const uint32_t use = (uint32_t)(g / kTmaStages);
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        const int64_t r0 = r_begin + g * kTmaRows;
+        const int rows = (int)min((int64_t)kTmaRows, r_end - r0);
+        mbar_expect_tx(&full[s], rows * row_bytes);
+        float* dst = tiles + (size_t)s * kTmaRows * kTmaCols;
+        for (int i = 0; i < rows; ++i) bulk_load(dst + (size_t)i * kTmaCols, X + (r0 + i) * row_stride + col0, row_bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int64_t col = col0 + (int64_t)tid * 4;
+  const bool active = col < D;
+  float m[4], c1[4], c0[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float sg = active ? __ldg(sigma + col + c) : 1.0f;
+    m[c] = active ? __ldg(mu + col + c) : 0.0f;
+    if (form == EVOK_GRAD_EXP) {
+      c1[c] = __fdiv_rn(1.0f, sg * sg);
+      c0[c] = 1.0f;
+    } else if (form == EVOK_GRAD_MOMENTS) {
+      c1[c] = 1.0f;
+      c0[c] = 0.0f;
+    } else {
+      c1[c] = __fdiv_rn(1.0f, sg);
+      c0[c] = sg;
+    }
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int64_t g = 0; g < n_groups; ++g) {
+    const int s = (int)(g % kTmaStages);
+    const uint32_t use = (uint32_t)(g / kTmaStages);
+    const int64_t r0 = r_begin + g * kTmaRows;
+    const int rows = (int)min((int64_t)kTmaRows, r_end - r0);
+    float a[kTmaRows], b[kTmaRows];
+#pragma unroll
+    for (int i = 0; i < kTmaRows; ++i) {
+      a[i] = b[i] = 0.0f;
+      if (i < rows) {
+        if (SYM) {
+          const float wp = __ldg(w + 2 * (r0 + i)), wm = __ldg(w + 2 * (r0 + i) + 1);
+          a[i] = 0.5f * (wp - wm);
+          b[i] = 0.5f * (wp + wm);
+        } else {
+          a[i] = b[i] = __ldg(w + r0 + i);
+        }
+      }
+    }
+    mbar_wait(&full[s], use & 1);
+    const float4* tile = reinterpret_cast<const float4*>(tiles + (size_t)s * kTmaRows * kTmaCols) + tid;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < kTmaRows; ++i) {
+        if (i < rows) {
+          const float4 v = tile[(size_t)i * (kTmaCols / 4)];
+          const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float e = x[c] - m[c];
+            s1[c] = fmaf(a[i], e, s1[c]);
+            s2[c] = fmaf(b[i], fmaf(e * e, c1[c], -c0[c]), s2[c]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (active) {
+    float* p1 = partial + ((int64_t)blockIdx.y * 2 + 0) * D + col;
+    float* p2 = partial + ((int64_t)blockIdx.y * 2 + 1) * D + col;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      p1[c] = s1[c];
+      p2[c] = s2[c];
+    }
+  }
+}
+
 struct GradPlan {
   int vec, tx, n_coltiles, n_chunks;
   int64_t units_per_chunk;
@@ -182,7 +363,7 @@ static GradPlan plan_grad(int64_t n_units, int64_t D, bool vec_ok) {
   while (p.tx < kGradThreads && p.tx < col_threads) p.tx <<= 1;
   p.n_coltiles = (int)((col_threads + p.tx - 1) / p.tx);
   const int ty = kGradThreads / p.tx;
-  int64_t chunks = kMaxResidentCtas / 2 / p.n_coltiles;  // ~4 CTAs per SM, one wave
+  int64_t chunks = (int64_t)kNumSMs * EVOK_GRAD_CTAS_PER_SM / p.n_coltiles;  // one wave of resident CTAs
   const int64_t max_useful = (n_units + (int64_t)ty * kGradUnroll - 1) / ((int64_t)ty * kGradUnroll);
   if (chunks > max_useful) chunks = max_useful;
   if (chunks < 1) chunks = 1;
@@ -197,9 +378,10 @@ template <int VEC, bool SYM, bool REGEN>
 static void launch_partial(const GradPlan& p, int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma,
                            int64_t n_units, int64_t D, uint64_t unit0, uint64_t seed, uint64_t stream_id, float* partial, cudaStream_t st) {
   dim3 grid(p.n_coltiles, p.n_chunks);
+  const PhiloxKey key = make_philox_key(seed, stream_id);
 #define EVOK_LAUNCH_TX(TXV)                                                                                                         \
   grad_partial_kernel<VEC, TXV, SYM, REGEN><<<grid, kGradThreads, 0, st>>>(form, X, ldx, w, mu, sigma, n_units, D, p.units_per_chunk, \
-                                                                           unit0, seed, stream_id, partial)
+                                                                           unit0, key, partial)
   switch (p.tx) {
     case 32: EVOK_LAUNCH_TX(32); break;
     case 64: EVOK_LAUNCH_TX(64); break;
@@ -228,6 +410,30 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
   if (n_units == 0) {
     cudaMemsetAsync(out_mu, 0, (size_t)D * 4, st);
     cudaMemsetAsync(out_sigma, 0, (size_t)D * 4, st);
+    return 0;
+  }
+  static const int use_tma = [] {
+    const char* e = getenv("EVOK_GRAD_TMA");
+    return e ? atoi(e) : EVOK_GRAD_TMA_DEFAULT;
+  }();
+  if (use_tma && !regen && vec_ok && form != EVOK_GRAD_MOMENTS && D >= 512 && n_units >= 4096) {
+    const int n_coltiles = (int)((D + kTmaCols - 1) / kTmaCols);
+    int64_t chunks = (int64_t)kNumSMs * EVOK_GRAD_TMA_CTAS_PER_SM / n_coltiles;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    const int64_t upc = (n_units + chunks - 1) / chunks;
+    const int n_chunks = (int)((n_units + upc - 1) / upc);
+    dim3 grid(n_coltiles, n_chunks);
+    if (sym) {
+      cudaFuncSetAttribute(grad_partial_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes);
+      grad_partial_tma_kernel<true><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(form, X, ldx, w, mu, sigma, n_units, D, upc, partial);
+    } else {
+      cudaFuncSetAttribute(grad_partial_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes);
+      grad_partial_tma_kernel<false><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(form, X, ldx, w, mu, sigma, n_units, D, upc, partial);
+    }
+    EVOK_CHECK_LAUNCH();
+    grad_finalize_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(partial, n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
+    EVOK_CHECK_LAUNCH();
     return 0;
   }
   if (regen) {

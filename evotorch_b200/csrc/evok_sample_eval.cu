@@ -18,12 +18,72 @@ static int sm_count() {
   return g_sm_count;
 }
 
-constexpr int kSampleThreads = 256;
+// tunables (profiles/ records the sweep that chose the defaults)
+#ifndef EVOK_SAMPLE_THREADS
+#define EVOK_SAMPLE_THREADS 256
+#endif
+#ifndef EVOK_SAMPLE_MINB
+#define EVOK_SAMPLE_MINB 3
+#endif
+#ifndef EVOK_SAMPLE_UNR
+#define EVOK_SAMPLE_UNR 2
+#endif
+#ifndef EVOK_SAMPLEONLY_MINB
+#define EVOK_SAMPLEONLY_MINB 5
+#endif
+#ifndef EVOK_SAMPLEONLY_UNR
+#define EVOK_SAMPLEONLY_UNR 1
+#endif
+constexpr int kSampleThreads = EVOK_SAMPLE_THREADS;
+// the fused kernels are issue/XU bound (two independent Philox chains per lane help); the sample-only kernel is store
+// bound and prefers occupancy (kbench sweep in profiles/)
+template <int OBJ>
+struct SampleTune {
+  static constexpr int kUnroll = OBJ == EVOK_OBJ_NONE ? EVOK_SAMPLEONLY_UNR : EVOK_SAMPLE_UNR;
+  static constexpr int kMinBlocks = OBJ == EVOK_OBJ_NONE ? EVOK_SAMPLEONLY_MINB : EVOK_SAMPLE_MINB;
+};
+
+// one column group (4 columns) of one unit: sample, store, accumulate
+template <int OBJ, bool SYM, bool STORE, bool VEC>
+__device__ __forceinline__ void sample_group(const PhiloxKey& key, uint64_t unit, uint32_t q, int64_t D,
+                                             const float* __restrict__ mu, const float* __restrict__ sigma, float* xp, float* xm,
+                                             ObjAcc<OBJ>& accp, ObjAcc<OBJ>& accm) {
+  float z[4];
+  normals4(key, unit, q, z);
+  const int64_t j = (int64_t)q << 2;
+  if (VEC) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu + j));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(sigma + j));
+    const float p0 = fmaf(s.x, z[0], m.x), p1 = fmaf(s.y, z[1], m.y), p2 = fmaf(s.z, z[2], m.z), p3 = fmaf(s.w, z[3], m.w);
+    if (STORE) st_stream4(xp + j, p0, p1, p2, p3);
+    accp.add(p0); accp.add(p1); accp.add(p2); accp.add(p3);
+    if (SYM) {
+      const float n0 = fmaf(-s.x, z[0], m.x), n1 = fmaf(-s.y, z[1], m.y), n2 = fmaf(-s.z, z[2], m.z), n3 = fmaf(-s.w, z[3], m.w);
+      if (STORE) st_stream4(xm + j, n0, n1, n2, n3);
+      accm.add(n0); accm.add(n1); accm.add(n2); accm.add(n3);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (j + c < D) {
+        const float m = __ldg(mu + j + c), s = __ldg(sigma + j + c);
+        const float p = fmaf(s, z[c], m);
+        if (STORE) st_stream1(xp + j + c, p);
+        accp.add(p);
+        if (SYM) {
+          const float n = fmaf(-s, z[c], m);
+          if (STORE) st_stream1(xm + j + c, n);
+          accm.add(n);
+        }
+      }
+    }
+  }
+}
 
 template <int OBJ, bool SYM, bool STORE, bool VEC>
-__global__ void __launch_bounds__(kSampleThreads)
+__global__ void __launch_bounds__(kSampleThreads, SampleTune<OBJ>::kMinBlocks)
     sample_eval_kernel(float* __restrict__ X, int64_t ldx, const float* __restrict__ mu, const float* __restrict__ sigma,
-                       int64_t row0, int64_t n_units, int64_t D, uint64_t seed, uint64_t stream_id, float* __restrict__ f) {
+                       int64_t row0, int64_t n_units, int64_t D, const __grid_constant__ PhiloxKey key, float* __restrict__ f) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (kSampleThreads / 32);
   const int64_t gw = (int64_t)blockIdx.x * (kSampleThreads / 32) + (threadIdx.x >> 5);
@@ -35,38 +95,18 @@ __global__ void __launch_bounds__(kSampleThreads)
     const int64_t r = SYM ? 2 * u : u;
     float* xp = STORE ? X + r * ldx : nullptr;
     float* xm = STORE ? xp + ldx : nullptr;
-    for (uint32_t q = lane; q < nq; q += 32) {
-      float z[4];
-      normals4(seed, stream_id, unit0 + (uint64_t)u, q, z);
-      const int64_t j = (int64_t)q << 2;
-      if (VEC) {
-        const float4 m = __ldg(reinterpret_cast<const float4*>(mu + j));
-        const float4 s = __ldg(reinterpret_cast<const float4*>(sigma + j));
-        const float p0 = fmaf(s.x, z[0], m.x), p1 = fmaf(s.y, z[1], m.y), p2 = fmaf(s.z, z[2], m.z), p3 = fmaf(s.w, z[3], m.w);
-        if (STORE) st_stream4(xp + j, p0, p1, p2, p3);
-        accp.add(p0); accp.add(p1); accp.add(p2); accp.add(p3);
-        if (SYM) {
-          const float n0 = fmaf(-s.x, z[0], m.x), n1 = fmaf(-s.y, z[1], m.y), n2 = fmaf(-s.z, z[2], m.z), n3 = fmaf(-s.w, z[3], m.w);
-          if (STORE) st_stream4(xm + j, n0, n1, n2, n3);
-          accm.add(n0); accm.add(n1); accm.add(n2); accm.add(n3);
-        }
-      } else {
+    const uint64_t unit = unit0 + (uint64_t)u;
+    constexpr int kSampleUnroll = SampleTune<OBJ>::kUnroll;
+    uint32_t q = lane;
+    if (kSampleUnroll > 1) {
+      // independent Philox chains in flight per lane
+      for (; q + 32u * (kSampleUnroll - 1) < nq; q += 32u * kSampleUnroll) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (j + c < D) {
-            const float m = __ldg(mu + j + c), s = __ldg(sigma + j + c);
-            const float p = fmaf(s, z[c], m);
-            if (STORE) st_stream1(xp + j + c, p);
-            accp.add(p);
-            if (SYM) {
-              const float n = fmaf(-s, z[c], m);
-              if (STORE) st_stream1(xm + j + c, n);
-              accm.add(n);
-            }
-          }
-        }
+        for (int uu = 0; uu < kSampleUnroll; ++uu)
+          sample_group<OBJ, SYM, STORE, VEC>(key, unit, q + 32u * uu, D, mu, sigma, xp, xm, accp, accm);
       }
     }
+    for (; q < nq; q += 32) sample_group<OBJ, SYM, STORE, VEC>(key, unit, q, D, mu, sigma, xp, xm, accp, accm);
     if (OBJ != EVOK_OBJ_NONE) {
       const float fp = accp.finish(D);
       float fm = 0.f;
@@ -130,12 +170,13 @@ static int launch_sample(float* X, int64_t ldx, const float* mu, const float* si
   const int64_t n_units = SYM ? n_rows / 2 : n_rows;
   const bool vec = (D % 4 == 0) && aligned16(mu) && aligned16(sigma) && (!STORE || (aligned16(X) && ldx % 4 == 0));
   const int64_t ctas_needed = (n_units + (kSampleThreads / 32) - 1) / (kSampleThreads / 32);
+  const PhiloxKey key = make_philox_key(seed, stream_id);
   if (vec) {
     auto k = sample_eval_kernel<OBJ, SYM, STORE, true>;
-    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, seed, stream_id, f);
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, f);
   } else {
     auto k = sample_eval_kernel<OBJ, SYM, STORE, false>;
-    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, seed, stream_id, f);
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, f);
   }
   EVOK_CHECK_LAUNCH();
   return 0;

@@ -103,6 +103,12 @@ def sample_eval(objective: int, X: Optional[torch.Tensor], mu: torch.Tensor, sig
         ldx = X.stride(0)
     if f is not None:
         _vec(f, "f", n_rows)
+    if objective != OBJ_NONE and f is None:
+        raise ValueError("f: a fitness buffer is required when an objective is fused into the sampler")
+    if symmetric and (n_rows % 2 or row0 % 2):
+        raise ValueError("symmetric sampling needs an even number of rows and an even first row")
+    if n_rows == 0:
+        return
     with _timed("sample_eval" if objective != OBJ_NONE else "sample"):
         rc = nat.lib().evok_sample_eval(objective, nat.ptr(X), ldx, mu.data_ptr(), sigma.data_ptr(), row0, n_rows, D, int(symmetric),
                                         seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, nat.ptr(f), nat.stream_of(mu))

@@ -47,12 +47,12 @@ def argsort_for_ranking(f: np.ndarray, higher_is_better: bool) -> np.ndarray:
     if higher_is_better:
         # ascending, stable; NaN last
         return np.argsort(f, kind="stable").astype(np.int64)
-    # descending, stable: NaN first (largest), ties keep ascending index order.
-    n = len(f)
-    key = -f.astype(np.float64)  # exact negation; -NaN stays NaN -> would sort last
-    nan = np.isnan(key)
-    key[nan] = -np.inf  # largest original value -> first position in descending order
-    return np.argsort(key, kind="stable").astype(np.int64) if n else np.zeros(0, np.int64)
+    # descending, stable: NaN (the largest value, above +inf) first, then by decreasing value; ties keep ascending index.
+    nan = np.isnan(f)
+    idx_nan = np.flatnonzero(nan)
+    idx_rest = np.flatnonzero(~nan)
+    order_rest = idx_rest[np.argsort(-f[idx_rest].astype(np.float64), kind="stable")]
+    return np.concatenate([idx_nan, order_rest]).astype(np.int64)
 
 
 def rank_centered(f, higher_is_better: bool) -> np.ndarray:
