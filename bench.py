@@ -313,7 +313,14 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    except BaseException:
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
