@@ -40,6 +40,8 @@ _SIGNATURES = {
     "evok_axpy": (c_int, [_P, c_int64, c_float, _P, _P]),
     "evok_sigma_update": (c_int, [_P, _P, c_int64, c_float, c_int, _P, c_float, _P, c_float, _P, c_float, _P]),
     "evok_cem_finalize": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "evok_mlp_parameter_length": (c_int64, [c_int, _P]),
+    "evok_mlp_forward": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -271,3 +271,32 @@ def cem_finalize(s1: torch.Tensor, s2: torch.Tensor, sigma: torch.Tensor, num_el
     nat.check(nat.lib().evok_cem_finalize(s1.data_ptr(), s2.data_ptr(), sigma.data_ptr(), D, num_elites, gm.data_ptr(), gs.data_ptr(),
                                           nat.stream_of(sigma)), "evok_cem_finalize")
     return gm, gs
+
+
+# ------------------------------------------------------------------------------------------------ K8
+ACT_IDS = {"none": 0, "identity": 0, "tanh": 1, "relu": 2, "sigmoid": 3}
+
+
+def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched policy forward: row i of `params` (flat Linear-layer parameters) applied to row i of `obs`."""
+    import ctypes
+
+    _mat(params, "parameters"); _mat(obs, "observations")
+    n = params.shape[0]
+    dims = [int(d) for d in dims]
+    act_ids = [ACT_IDS[a] if isinstance(a, str) else int(a) for a in acts]
+    if obs.shape != (n, dims[0]):
+        raise ValueError(f"observations: expected shape {(n, dims[0])}, got {tuple(obs.shape)}")
+    if out is None:
+        out = torch.empty(n, dims[-1], dtype=torch.float32, device=params.device)
+    _mat(out, "out")
+    d_arr = (ctypes.c_int32 * len(dims))(*dims)
+    a_arr = (ctypes.c_int32 * len(act_ids))(*act_ids)
+    need = nat.lib().evok_mlp_parameter_length(len(act_ids), d_arr)
+    if params.shape[1] != need:
+        raise ValueError(f"parameters: expected {need} columns for layer widths {dims}, got {params.shape[1]}")
+    with _timed("mlp_forward"):
+        rc = nat.lib().evok_mlp_forward(params.data_ptr(), params.stride(0), obs.data_ptr(), obs.stride(0), out.data_ptr(), out.stride(0), n,
+                                        len(act_ids), d_arr, a_arr, nat.stream_of(params))
+    nat.check(rc, "evok_mlp_forward")
+    return out

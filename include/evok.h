@@ -165,6 +165,22 @@ int evok_sigma_update(float* sigma, const float* g, int64_t D, float lr, int exp
 int evok_cem_finalize(const float* s1, const float* s2, const float* sigma, int64_t D, int64_t num_elites,
                       float* grad_mu, float* grad_sigma, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K8: batched flat-parameter MLP policy forward, one observation per policy.
+ * Replaces Policy.__call__ (neuroevolution/net/vecrl.py:1240-1279: vmap(functional_call) over the rows of the
+ * N x L parameter matrix set by set_parameters) for feed-forward nets made of Linear layers + activations.
+ * Parameter row layout (net/functional.py:118-129): per layer W (out x in, row-major) then b (out).
+ *   out[i, :] = layer_{n-1}(... act_0(W_0 obs[i, :] + b_0) ...)        acts: EVOK_ACT_* applied after each layer
+ * dims_host: n_layers + 1 layer widths (host array); acts_host: n_layers activation ids (host array).
+ * --------------------------------------------------------------------------------------------- */
+#define EVOK_ACT_NONE 0
+#define EVOK_ACT_TANH 1
+#define EVOK_ACT_RELU 2
+#define EVOK_ACT_SIGMOID 3
+int64_t evok_mlp_parameter_length(int n_layers, const int32_t* dims_host);
+int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
+                     int n_layers, const int32_t* dims_host, const int32_t* acts_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,24 @@ for path in libs:
                     "lazy_eval_ms": t_lazy, "grad_ms": t_g, "grad_gbs": 0.5 * gb / t_g * 1e3}
     print(f"{tag:28s} sample_eval {t_se:7.3f} ms {gb / t_se * 1e3:7.0f} GB/s | sample {t_s:7.3f} ms {gb / t_s * 1e3:7.0f} GB/s | "
           f"lazy {t_lazy:7.3f} ms | grad {t_g:7.3f} ms {0.5 * gb / t_g * 1e3:7.0f} GB/s (rel diff vs default {gdiff:.1e})", flush=True)
+# K8 at BASELINE config 4: 65 536 policies x 100 881 parameters (26.4 GB), one observation each
+del X, f, w
+torch.cuda.empty_cache()
+NP, dims, acts = 65536, [376, 256, 17], [1, 0]
+L = 376 * 256 + 256 + 256 * 17 + 17
+P = torch.empty(NP, L, device=dev).normal_(0, 0.1)
+obs = torch.randn(NP, 376, device=dev)
+out = torch.empty(NP, 17, device=dev)
+h = load(os.path.join(ROOT, "evotorch_b200", "lib", "libevok.so"))
+d_arr, a_arr = (ctypes.c_int32 * 3)(*dims), (ctypes.c_int32 * 2)(*acts)
+t_mlp = timeit(lambda: h.evok_mlp_forward(P.data_ptr(), L, obs.data_ptr(), 376, out.data_ptr(), 17, NP, 2, d_arr, a_arr, stream))
+print(f"mlp_forward cfg4 (65536 x 100881, B=1): {t_mlp:7.3f} ms  {4.0 * NP * L / 1e9 / t_mlp * 1e3:7.0f} GB/s", flush=True)
+results["_mlp_cfg4"] = {"ms": t_mlp, "gbs": 4.0 * NP * L / 1e9 / t_mlp * 1e3}
+ref_t = timeit(lambda: torch.bmm(P[:, :376 * 256].view(NP, 256, 376), obs.unsqueeze(-1)))
+print(f"torch.bmm layer-1 only: {ref_t:7.3f} ms  {4.0 * NP * 376 * 256 / 1e9 / ref_t * 1e3:7.0f} GB/s")
+del P, obs, out
+torch.cuda.empty_cache()
+X = torch.empty(N, D, device=dev)
 # reference points: torch copy (read+write) and torch fill (write only)
 Y = torch.empty_like(X[: N // 2])
 t_copy = timeit(lambda: Y.copy_(X[: N // 2]))

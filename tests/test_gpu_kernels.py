@@ -497,6 +497,42 @@ def test_cmaes_on_cuda_reproduces_reference_trajectory(golden):
     assert c2.status["mean_eval"] < 0.2 * m0
 
 
+# ---------------------------------------------------------------------------------------------- K8 batched policy forward
+def test_policy_kernel_matches_reference_golden_and_oracle(golden):
+    from evotorch_b200.neuroevolution import Policy
+
+    net = torch.nn.Sequential(torch.nn.Linear(11, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3))
+    pol = Policy(net)
+    pol.set_parameters(C(golden["policy/params"]))
+    close(N(pol(C(golden["policy/obs"]))), golden["policy/act"], rtol=1e-5, atol=2e-6)  # the reference's vmap(functional_call)
+    rng = np.random.default_rng(0)
+    for dims, acts, n in (([376, 256, 17], ["tanh", "none"], 67), ([5, 1], ["none"], 9), ([33, 70, 9, 4], ["relu", "sigmoid", "tanh"], 40),
+                          ([2048, 3, 2048], ["tanh", "none"], 3)):
+        L = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(acts)))
+        P = (rng.standard_normal((n, L)) * 0.1).astype(np.float32)
+        X = rng.standard_normal((n, dims[0])).astype(np.float32)
+        got = N(ops.mlp_forward(C(P), C(X), dims, acts))
+        h = X.astype(np.float64)
+        off = 0
+        for l, act in enumerate(acts):
+            W = P[:, off:off + dims[l] * dims[l + 1]].reshape(n, dims[l + 1], dims[l]).astype(np.float64)
+            off += dims[l] * dims[l + 1]
+            b = P[:, off:off + dims[l + 1]].astype(np.float64)
+            off += dims[l + 1]
+            h = np.einsum("noi,ni->no", W, h) + b
+            h = {"tanh": np.tanh, "relu": lambda v: np.maximum(v, 0), "sigmoid": lambda v: 1 / (1 + np.exp(-v)), "none": lambda v: v}[act](h)
+        close(got, h, rtol=2e-5, atol=2e-5)
+        if dims == [376, 256, 17]:
+            assert L == 100881  # cfg4: rows are only 4-byte aligned (L is odd)
+            close(got, O.mlp_policy_forward(P, X, 376, 256, 17, "tanh"), rtol=2e-5, atol=2e-5)
+            net4 = torch.nn.Sequential(torch.nn.Linear(376, 256), torch.nn.Tanh(), torch.nn.Linear(256, 17))
+            p4 = Policy(net4)
+            p4.set_parameters(C(P))
+            close(N(p4(C(X))), got, rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        ops.mlp_forward(C(np.zeros((3, 10))), C(np.zeros((3, 5))), [5, 1], ["none"])
+
+
 # ---------------------------------------------------------------------------------------------- full-size properties
 def test_config2_size_properties():
     """BASELINE configs[1]: PGPE, Rastrigin, N = 100 000, D = 10 000 (4 GB population) -- size-independent properties."""

@@ -263,3 +263,23 @@ def test_cmaes_cpu_trajectory_matches_reference(golden):
     m0 = sep.status["mean_eval"]
     sep.run(40)
     assert sep.status["mean_eval"] < m0 and sep.C.ndim == 1
+
+
+def test_policy_cpu_matches_reference(golden):
+    from evotorch_b200.neuroevolution import Policy, count_parameters, fill_parameters, parameter_vector
+
+    net = torch.nn.Sequential(torch.nn.Linear(11, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3))
+    pol = Policy(net)
+    assert pol.parameter_length == int(golden["policy/dims"][3]) == count_parameters(net)
+    pol.set_parameters(T(golden["policy/params"]))
+    np.testing.assert_allclose(pol(T(golden["policy/obs"])).numpy(), golden["policy/act"], rtol=1e-5, atol=2e-6)
+    # one shared flat vector == filling the module (the reference's tests/test_net.py idea)
+    flat = T(golden["policy/params"][0])
+    pol.set_parameters(flat)
+    fill_parameters(net, flat)
+    np.testing.assert_allclose(pol(T(golden["policy/obs"])).numpy(), net(T(golden["policy/obs"])).detach().numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(parameter_vector(net), flat)
+    with pytest.raises(ValueError):
+        pol.set_parameters(torch.zeros(5))
+    with pytest.raises(ValueError):
+        Policy(net)(torch.zeros(2, 11))
