@@ -34,38 +34,65 @@ __device__ __forceinline__ float activate(float v, int act) {
   }
 }
 
+// Activations live in shared memory SHIFTED by the 16-byte phase of the layer's weight rows: if every neuron row of a layer
+// starts `ph` floats past a 16-byte boundary (true for all rows of a layer whenever n_in % 4 == 0), lane l loads the ALIGNED
+// float4 chunks of the row and multiplies them with xs[4c .. 4c+3] where xs[u] = x[u - ph] and xs is zero outside the valid
+// range -- the `ph` leading floats of the first chunk (they belong to the previous neuron) and the trailing floats of the last
+// chunk meet zeros.  This turns 4-byte-aligned rows into 128-bit coalesced loads without any masking in the inner loop.
+// The first and the last policy row use the scalar path so that no load ever touches bytes outside the parameter matrix.
+constexpr int kMlpPad = 8;  // floats of zero padding in front of / behind an activation vector
+
+__device__ __forceinline__ void store_shifted(float* buf, int ph, int j, float v) { buf[kMlpPad + ph + j] = v; }
+
 __global__ void __launch_bounds__(kMlpThreads)
     mlp_forward_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ obs, int64_t ldo, float* __restrict__ out,
                        int64_t ldout, int64_t N, const __grid_constant__ MlpSpec spec) {
-  extern __shared__ float act_buf[];  // 2 x max_width
+  extern __shared__ __align__(16) float act_buf[];  // 2 x (max_width + 2 * kMlpPad)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stride = (spec.max_width + 2 * kMlpPad + 3) & ~3;  // keeps both ping-pong buffers 16-byte aligned
   for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
     const float* prow = params + i * ldp;
+    const bool edge_row = (i == 0) || (i == N - 1);
     float* cur = act_buf;
-    float* nxt = act_buf + spec.max_width;
-    for (int k = threadIdx.x; k < spec.dims[0]; k += kMlpThreads) cur[k] = ld_stream1(obs + i * ldo + k);
+    float* nxt = act_buf + stride;
+    // phase of layer 0's weight rows (floats past a 16-byte boundary)
+    int ph = (int)((reinterpret_cast<uintptr_t>(prow + spec.w_off[0]) >> 2) & 3);
+    for (int k = threadIdx.x; k < stride; k += kMlpThreads) cur[k] = 0.0f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < spec.dims[0]; k += kMlpThreads) store_shifted(cur, ph, k, ld_stream1(obs + i * ldo + k));
     __syncthreads();
     for (int l = 0; l < spec.n_layers; ++l) {
       const int n_in = spec.dims[l], n_out = spec.dims[l + 1];
       const float* W = prow + spec.w_off[l];
       const float* b = W + (int64_t)n_in * n_out;
       const bool last = l == spec.n_layers - 1;
+      const int ph_next = last ? 0 : (int)((reinterpret_cast<uintptr_t>(prow + spec.w_off[l + 1]) >> 2) & 3);
+      const bool vec = ((n_in & 3) == 0) && !edge_row;
+      // zero the destination (including its pads) before the neurons of this layer are written into it
+      if (!last)
+        for (int k = threadIdx.x; k < stride; k += kMlpThreads) nxt[k] = 0.0f;
+      __syncthreads();
+      const float* xs = cur + kMlpPad;  // xs[u] = x[u - ph]
+      const int nchunks = (n_in + ph + 3) >> 2;
       for (int j0 = warp * kMlpNeuronsPerPass; j0 < n_out; j0 += kMlpWarps * kMlpNeuronsPerPass) {
         float acc[kMlpNeuronsPerPass];
 #pragma unroll
         for (int t = 0; t < kMlpNeuronsPerPass; ++t) acc[t] = 0.0f;
         const int n_here = min(kMlpNeuronsPerPass, n_out - j0);
-        if (n_here == kMlpNeuronsPerPass) {
-          const float* w0 = W + (int64_t)j0 * n_in;
-          for (int k = lane; k < n_in; k += 32) {
-            const float x = cur[k];
+        if (vec && n_here == kMlpNeuronsPerPass) {
+          const float* w0 = W + (int64_t)j0 * n_in - ph;  // 16-byte aligned
+          for (int c = lane; c < nchunks; c += 32) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xs + 4 * c);
 #pragma unroll
-            for (int t = 0; t < kMlpNeuronsPerPass; ++t) acc[t] = fmaf(ld_stream1(w0 + (int64_t)t * n_in + k), x, acc[t]);
+            for (int t = 0; t < kMlpNeuronsPerPass; ++t) {
+              const float4 w4 = ld_stream4(w0 + (int64_t)t * n_in + 4 * c);
+              acc[t] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[t]))));
+            }
           }
         } else {
           for (int t = 0; t < n_here; ++t) {
             const float* w0 = W + (int64_t)(j0 + t) * n_in;
-            for (int k = lane; k < n_in; k += 32) acc[t] = fmaf(ld_stream1(w0 + k), cur[k], acc[t]);
+            for (int k = lane; k < n_in; k += 32) acc[t] = fmaf(ld_stream1(w0 + k), xs[ph + k], acc[t]);
           }
         }
 #pragma unroll
@@ -76,13 +103,14 @@ __global__ void __launch_bounds__(kMlpThreads)
           for (int t = 1; t < kMlpNeuronsPerPass; ++t) v = lane == t ? acc[t] : v;
           v = activate(v + ld_stream1(b + j0 + lane), spec.acts[l]);
           if (last) out[i * ldout + j0 + lane] = v;
-          else nxt[j0 + lane] = v;
+          else store_shifted(nxt, ph_next, j0 + lane, v);
         }
       }
       __syncthreads();
       float* tmp = cur;
       cur = nxt;
       nxt = tmp;
+      ph = ph_next;
     }
   }
 }
@@ -121,7 +149,7 @@ extern "C" EVOK_API int evok_mlp_forward(const float* params, int64_t ldp, const
   spec.max_width = maxw;
   if (ldp < off || ldo < spec.dims[0] || ldout < spec.dims[n_layers]) return EVOK_E_BADSIZE;
   if (N == 0) return 0;
-  const size_t smem = 2 * (size_t)maxw * sizeof(float);
+  const size_t smem = 2 * (size_t)((maxw + 2 * 8 + 3) & ~3) * sizeof(float);
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_forward_kernel, kMlpThreads, smem) != cudaSuccess || per_sm <= 0) per_sm = 4;
   int dev = 0, sms = kNumSMs;
