@@ -219,8 +219,18 @@ def run_ours(args):
     fused_ms = timers.get("sample_eval", (0, float("nan")))[1]
     fused_bytes = 4.0 * n_local * D + 4.0 * n_local
     achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
+    # DRAM traffic of the kernel from the committed ncu --set full capture (profiles/traffic.json), scaled by rows x columns
+    traffic, traffic_note = None, "no capture"
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            cap = json.load(fh)["sample_eval"]
+        traffic = cap["ratio"] * fused_bytes
+        traffic_note = (f"dram__bytes_read+write = {cap['ratio']:.4f} x algorithmic bytes in {cap['source']} "
+                        f"(captured at popsize {cap['capture']['popsize']}, scaled linearly to this launch)")
+    except Exception:
+        pass
     roofline = {"kernel": "evok::sample_eval_kernel<RASTRIGIN, symmetric, store, vec4>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
                 "share_of_step": fused_ms / (elapsed_ms / K)}
     if "grad" in timers:
