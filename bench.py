@@ -162,6 +162,9 @@ def run_ours(args):
     from evotorch_b200.optimizers import ClipUp
     from evotorch_b200.tools import modify_tensor
 
+    # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set in some images): keep stdout = the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

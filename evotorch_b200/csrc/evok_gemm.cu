@@ -1,0 +1,392 @@
+// K6 / K7: fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), for the dense contractions of
+// CMA-ES (cmaes.py:427 `Y = Z A^T`, :548 rank-mu update `Y^T diag(w) Y`) and XNES.
+//
+//   C[M x N] = A[M x K] * B[N x K]^T            (A, B row-major with K contiguous: "K-major"; fp32 in, fp32 out)
+//
+// Accuracy: every fp32 operand x is split as x = hi + lo with hi = x rounded down to TF32 (13 low mantissa bits cleared)
+// and lo = x - hi (exact); the kernel accumulates hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator with
+// tcgen05.mma.kind::tf32 ("3xTF32"), which restores ~2^-21 relative accuracy per product -- plain single-pass TF32 (2^-10)
+// would break the 1e-5 parity bar of the searchers' state.
+//
+// Structure (one CTA per 128 x 256 output tile, optional split-K over blockIdx.z):
+//   warp 0      TMA producer: 4 tile loads per K-block (A_hi, A_lo, B_hi, B_lo; 128-byte swizzle), 2-stage mbarrier ring
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (12 MMAs of 128 x 256 x 8 per K-block),
+//               tcgen05.commit releases the stage / signals the epilogue
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> 128-byte row segments to global memory,
+//               optional second output C2 = alpha * acc + bias[col] (X = m + sigma * Y)
+#include <cuda.h>
+
+#include "evok_common.cuh"
+
+namespace evok {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 256;
+constexpr int kGemmBK = 32;  // floats = 128 bytes = one swizzle span
+constexpr int kGemmStages = 2;
+constexpr int kGemmThreads = 192;
+constexpr int kUmmaK = 8;  // tf32: 32 bytes of K per MMA
+constexpr uint32_t kTileABytes = kGemmBM * kGemmBK * 4;  // 16 KB
+constexpr uint32_t kTileBBytes = kGemmBN * kGemmBK * 4;  // 32 KB
+constexpr uint32_t kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 96 KB
+constexpr size_t kGemmSmemBytes = (size_t)kGemmStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
+      "%28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor of a K-major tile stored as rows of 128 bytes with the 128-byte swizzle
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version(1)<<46 | layout(SWIZZLE_128B = 2)<<61)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: 8 rows x 128 B between core-matrix groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+
+struct GemmParams {
+  int M, N, K;
+  int kblocks_per_split;
+  float* C;
+  int64_t ldc;
+  int64_t split_stride;  // elements between the partial outputs of consecutive K splits
+  float* C2;             // optional second output alpha * acc + bias[col]
+  int64_t ldc2;
+  const float* alpha_dev;
+  const float* bias;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+  extern __shared__ unsigned char gemm_smem_raw[];
+  // tiles need 1024-byte alignment (swizzle atom)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)kGemmStages * kStageBytes);
+  uint64_t* empty = full + kGemmStages;
+  uint64_t* tmem_full = empty + kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
+  const int total_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int kb_begin = blockIdx.z * p.kblocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kblocks_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      bar_init(&full[s], 1);
+      bar_init(&empty[s], 1);
+    }
+    bar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kGemmBN);  // 256 fp32 columns x 128 lanes
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kGemmStages;
+        const uint32_t use = i / kGemmStages;
+        bar_wait(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
+        unsigned char* st = base + (size_t)s * kStageBytes;
+        bar_expect_tx(&full[s], kStageBytes);
+        const int kx = (kb_begin + i) * kGemmBK;
+        tma_load_2d(st, &map_a_hi, kx, m0, &full[s]);
+        tma_load_2d(st + kTileABytes, &map_a_lo, kx, m0, &full[s]);
+        tma_load_2d(st + 2 * kTileABytes, &map_b_hi, kx, n0, &full[s]);
+        tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kGemmStages;
+        const uint32_t use = i / kGemmStages;
+        bar_wait(&full[s], use & 1);
+        tc_fence_after();
+        const uint32_t st = s32(base + (size_t)s * kStageBytes);
+        const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + kTileABytes);
+        const uint64_t b_hi = make_sw128_desc(st + 2 * kTileABytes), b_lo = make_sw128_desc(st + 2 * kTileABytes + kTileBBytes);
+#pragma unroll
+        for (int k = 0; k < kGemmBK / kUmmaK; ++k) {
+          const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // advance the start address by 32 bytes per MMA along K
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, kIdesc, (i | k) != 0);
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, kIdesc, 1);
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, kIdesc, 1);
+        }
+        umma_commit(&empty[s]);  // stage reusable once these MMAs have consumed it
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    bar_wait(tmem_full, 0);
+    tc_fence_after();
+    const float alpha = (p.C2 && p.alpha_dev) ? *p.alpha_dev : 1.0f;
+    float* crow = p.C + (int64_t)blockIdx.z * p.split_stride + (int64_t)row * p.ldc;
+    float* c2row = p.C2 ? p.C2 + (int64_t)row * p.ldc2 : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+      if (num_kb <= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < p.M) {
+        const int col = n0 + c0;
+        if (col + 32 <= p.N && ((reinterpret_cast<uintptr_t>(crow + col) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + col + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col + j < p.N) crow[col + j] = __uint_as_float(r[j]);
+        }
+        if (c2row) {
+          for (int j = 0; j < 32; ++j)
+            if (col + j < p.N) c2row[col + j] = fmaf(alpha, __uint_as_float(r[j]), p.bias ? __ldg(p.bias + col + j) : 0.0f);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kGemmBN);
+  }
+}
+
+// ---- operand preparation -----------------------------------------------------------------------------------------
+// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols, float* __restrict__ hi,
+                                                         float* __restrict__ lo, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols, c = i % cols;
+  const float v = x[r * ldx + c];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[r * ldo + c] = h;
+  lo[r * ldo + c] = v - h;
+}
+
+// out[c, r] = (w ? w[r] : 1) * in[r, c]   (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) transpose_scale_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int64_t cols,
+                                                              const float* __restrict__ w, float* __restrict__ out, int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? in[r * ldi + c] * (w ? w[r] : 1.0f) : 0.0f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t c = c0 + k, r = r0 + tx;
+    if (c < cols && r < rows) out[c * ldo + r] = tile[tx][k];
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ partial, int splits, int64_t split_stride, int64_t M,
+                                                            int64_t N, int64_t ldp, float* __restrict__ C, int64_t ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int64_t r = i / N, c = i % N;
+  float acc = 0.0f;
+  for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * split_stride + r * ldp + c];
+  C[r * ldc + c] = acc;
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows x K], K contiguous (pitch ld floats); box = 32 floats (128 B) x box_rows; 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct GemmPlan {
+  int64_t ldk;  // pitch of the split operands (floats), multiple of 4
+  int splits, kblocks_per_split;
+  size_t off_a_hi, off_a_lo, off_b_hi, off_b_lo, off_partial, total;
+};
+
+static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, bool allow_split = true) {
+  GemmPlan g;
+  g.ldk = round_up(K, 4);
+  const int64_t tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
+  const int total_kb = (int)((K + kGemmBK - 1) / kGemmBK);
+  int splits = 1;
+  while (allow_split && tiles * splits * 2 <= kNumSMs && splits * 2 <= total_kb && splits < 16) splits *= 2;
+  g.kblocks_per_split = (total_kb + splits - 1) / splits;
+  g.splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
+  auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  g.off_a_hi = o; o += al((size_t)M * g.ldk * 4);
+  g.off_a_lo = o; o += al((size_t)M * g.ldk * 4);
+  g.off_b_hi = o; o += al((size_t)N * g.ldk * 4);
+  g.off_b_lo = o; o += al((size_t)N * g.ldk * 4);
+  g.off_partial = o; o += g.splits > 1 ? al((size_t)g.splits * M * N * 4) : 0;
+  g.total = o;
+  return g;
+}
+
+}  // namespace evok
+
+using namespace evok;
+
+extern "C" EVOK_API size_t evok_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1024;
+  return plan_gemm(M, N, K).total + 1024;
+}
+
+extern "C" EVOK_API int evok_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C,
+                                     int64_t ldc, float* C2, int64_t ldc2, const float* alpha_dev, const float* bias, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  if (!A || !B || !C || !ws) return EVOK_E_NULLPTR;
+  if (M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N || (C2 && ldc2 < N)) return EVOK_E_BADSIZE;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return EVOK_E_BADSIZE;
+  const GemmPlan g = plan_gemm(M, N, K, C2 == nullptr);  // the fused second output needs the whole K range in one CTA
+  char* w8 = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  if (ws_bytes < g.total + (size_t)(w8 - (char*)ws)) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* a_hi = (float*)(w8 + g.off_a_hi);
+  float* a_lo = (float*)(w8 + g.off_a_lo);
+  float* b_hi = (float*)(w8 + g.off_b_hi);
+  float* b_lo = (float*)(w8 + g.off_b_lo);
+  float* partial = (float*)(w8 + g.off_partial);
+  split_tf32_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, g.ldk);
+  split_tf32_kernel<<<(unsigned)((N * K + 255) / 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, g.ldk);
+  EVOK_CHECK_LAUNCH_N(2);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, M, K, g.ldk, kGemmBM))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo, M, K, g.ldk, kGemmBM))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, N, K, g.ldk, kGemmBN))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo, N, K, g.ldk, kGemmBN))) return rc;
+  GemmParams p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.kblocks_per_split = g.kblocks_per_split;
+  const bool split = g.splits > 1;
+  p.C = split ? partial : C;
+  p.ldc = split ? N : ldc;
+  p.split_stride = split ? M * N : 0;
+  p.C2 = split ? nullptr : C2;
+  p.ldc2 = ldc2;
+  p.alpha_dev = alpha_dev;
+  p.bias = bias;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
+      return (int)cudaGetLastError();
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((N + kGemmBN - 1) / kGemmBN), (unsigned)g.splits);
+  gemm_tf32x3_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  EVOK_CHECK_LAUNCH();
+  if (split) {
+    reduce_splits_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(partial, g.splits, M * N, M, N, N, C, ldc);
+    EVOK_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" EVOK_API int evok_transpose_scale(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out, int64_t ldo,
+                                             void* stream) {
+  if (!in || !out) return EVOK_E_NULLPTR;
+  if (rows <= 0 || cols <= 0 || ldi < cols || ldo < rows) return EVOK_E_BADSIZE;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  transpose_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, rows, cols, w, out, ldo);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}

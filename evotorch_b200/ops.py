@@ -300,3 +300,41 @@ def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Option
                                         len(act_ids), d_arr, a_arr, nat.stream_of(params))
     nat.check(rc, "evok_mlp_forward")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ K6 / K7
+def gemm_nt(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None, *, out2: Optional[torch.Tensor] = None,
+            alpha: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ B.T on the tensor cores with fp32 accuracy (3xTF32); optionally also out2 = alpha * C + bias (broadcast over rows)."""
+    _mat(A, "A"); _mat(B, "B")
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise ValueError(f"inner dimensions differ: {K} vs {K2}")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _mat(out, "out")
+    if out2 is not None:
+        _mat(out2, "out2")
+    if bias is not None:
+        _vec(bias, "bias", N)
+    nbytes = nat.lib().evok_gemm_workspace_bytes(M, N, K)
+    ws = nat.workspace(A.device, nbytes, "gemm")
+    with _timed("gemm"):
+        rc = nat.lib().evok_gemm_nt(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, out.data_ptr(), out.stride(0), nat.ptr(out2),
+                                    0 if out2 is None else out2.stride(0), nat.ptr(alpha), nat.ptr(bias), ws.data_ptr(), ws.numel(),
+                                    nat.stream_of(A))
+    nat.check(rc, "evok_gemm_nt")
+    return out
+
+
+def transpose_scale(X: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(w[:, None] * X).T as a new row-major matrix."""
+    _mat(X, "X")
+    rows, cols = X.shape
+    if w is not None:
+        _vec(w, "w", rows)
+    out = torch.empty(cols, rows, dtype=torch.float32, device=X.device)
+    nat.check(nat.lib().evok_transpose_scale(X.data_ptr(), X.stride(0), rows, cols, nat.ptr(w), out.data_ptr(), out.stride(0),
+                                             nat.stream_of(X)), "evok_transpose_scale")
+    return out

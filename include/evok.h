@@ -181,6 +181,21 @@ int64_t evok_mlp_parameter_length(int n_layers, const int32_t* dims_host);
 int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
                      int n_layers, const int32_t* dims_host, const int32_t* acts_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K6 / K7: fp32-accurate tensor-core GEMM (tcgen05 + TMEM + TMA, 3xTF32 operand splitting).
+ *   C[M x N] = A[M x K] * B[N x K]^T        A, B, C row-major fp32 (lda, ldb >= K; ldc >= N)
+ *   optional C2[M x N] = alpha_dev[0] * (A B^T) + bias[col]    (C2 / alpha_dev / bias nullable)
+ * Replaces the dense contractions of CMA-ES: `ys = (A @ zs.T).T`, `xs = m + sigma * ys` (cmaes.py:427-429; call with
+ * A = zs, B = A_chol, C = ys, C2 = xs, alpha_dev = &sigma, bias = m) and the rank-mu update
+ * sum_i w_i y_i y_i^T (cmaes.py:548; call with A = (w * Y)^T, B = Y^T built by evok_transpose_scale), and XNES'
+ * `A z^T` / sum_i w_i z_i z_i^T (distributions.py:938, :980-984).
+ * --------------------------------------------------------------------------------------------- */
+size_t evok_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int evok_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                 float* C2, int64_t ldc2, const float* alpha_dev, const float* bias, void* ws, size_t ws_bytes, void* stream);
+/* out[c, r] = (w ? w[r] : 1) * in[r, c]: builds the K-major operands of the weighted SYRK */
+int evok_transpose_scale(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
