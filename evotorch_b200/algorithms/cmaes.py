@@ -7,8 +7,9 @@ Per generation (cmaes.py:567-606):
     weighted recombinations sum_i w_i z_i, sum_i w_i y_i (K4 weighted column sums)
     evolution paths, sigma, rank-1 + rank-mu update of C, Cholesky.
 The rank-mu term is computed as Y^T diag(w) Y (a weighted SYRK): the reference materialises an N x D x D broadcast
-temporary (cmaes.py:548; 16 GiB at D = 1024, N = 4096).  Dense contractions currently go to the GEMM library
-(torch.matmul / cuBLAS, torch.linalg.cholesky / cuSOLVER): the hand-written tcgen05 kernels are the next row in DESIGN.md.
+temporary (cmaes.py:548; 16 GiB at D = 1024, N = 4096).  On CUDA fp32 both contractions run on the hand-written tcgen05
+kernel (csrc/evok_gemm.cu: TMA -> 128B-swizzled smem -> tcgen05.mma.kind::tf32 with 3xTF32 operand splitting -> TMEM ->
+register accumulation); the Cholesky factorisation stays on cuSOLVER (torch.linalg.cholesky).
 """
 
 from __future__ import annotations
@@ -149,6 +150,12 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             problem.make_gaussian(out=zs)
         if self.separable:
             ys = self.A.unsqueeze(0) * zs
+        elif ops.uses_kernels(zs) and ops.uses_kernels(self.A):
+            # K6: one tcgen05 GEMM (3xTF32, fp32-accurate) with the affine epilogue xs = m + sigma * ys fused in
+            ys = torch.empty_like(zs)
+            xs = torch.empty_like(zs)
+            ops.gemm_nt(zs, self.A.contiguous(), ys, out2=xs, alpha=self.sigma.reshape(1), bias=self.m.contiguous())
+            return zs, ys, xs
         else:
             ys = zs @ self.A.T
         xs = self.m.unsqueeze(0) + self.sigma * ys
@@ -215,7 +222,12 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         else:
             pc = weighted_pc * self.p_c
             r1_update = c1a * (torch.outer(pc, pc) - self.C)
-            rmu_update = self.c_mu * ((ys.T * assigned_weights) @ ys - self._weights_sum * self.C)  # weighted SYRK, no NxDxD temp
+            if ops.uses_kernels(ys) and ops.uses_kernels(assigned_weights):
+                # K7: weighted SYRK Y^T diag(w) Y as one tcgen05 GEMM over K-major (w*Y)^T and Y^T (split-K over the population)
+                syrk = ops.gemm_nt(ops.transpose_scale(ys.contiguous(), assigned_weights.contiguous()), ops.transpose_scale(ys.contiguous()))
+            else:
+                syrk = (ys.T * assigned_weights) @ ys  # no N x D x D temporary either
+            rmu_update = self.c_mu * (syrk - self._weights_sum * self.C)
         self.C = self.C + r1_update + rmu_update
 
     def _limit_stdev(self) -> None:

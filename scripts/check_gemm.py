@@ -15,7 +15,7 @@ for (M, N, K) in [(128, 256, 32), (128, 256, 64), (128, 256, 1024), (256, 512, 9
     torch.cuda.synchronize()
     err = float((C.double() - ref).abs().max() / ref.abs().max())
     t32 = float(((A @ B.T).double() - ref).abs().max() / ref.abs().max())
-    good = err < 2e-6
+    good = err < 3e-6
     ok &= good
     print(f"M={M} N={N} K={K}: max rel err {err:.2e} (torch fp32 matmul {t32:.2e}) {'OK' if good else 'FAIL'}", flush=True)
 # fused second output
@@ -26,7 +26,7 @@ C2 = torch.empty(M, N, device=dev)
 C = ops.gemm_nt(A, B, out2=C2, alpha=alpha, bias=bias)
 ref = A.double() @ B.double().T
 e2 = float((C2.double() - (0.37 * ref + bias.double())).abs().max() / ref.abs().max())
-print("fused epilogue rel err", e2); ok &= e2 < 2e-6
+print("fused epilogue rel err", e2); ok &= e2 < 3e-6
 # transpose_scale
 Y = torch.randn(300, 70, device=dev); w = torch.randn(300, device=dev)
 T = ops.transpose_scale(Y, w)

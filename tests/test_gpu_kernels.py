@@ -462,6 +462,32 @@ def test_user_objective_and_torch_rng_paths_on_cuda():
     close(N(X[0::2] + X[1::2]), np.broadcast_to(2 * N(st.status["center"]), (250, 64)), rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (4096, 1024, 1024), (1024, 1024, 4096), (100, 70, 36), (129, 257, 40), (12, 6, 6), (300, 513, 1000)])
+def test_tcgen05_gemm_matches_float64(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    ref = A.double() @ B.double().T
+    C = ops.gemm_nt(A, B)
+    scale = float(ref.abs().max())
+    assert float((C.double() - ref).abs().max()) / scale < 3e-6  # fp32-SGEMM-class accuracy out of TF32 tensor cores (3xTF32)
+    # exactly representable data must come out exact: proves the TMA / swizzle / descriptor data path
+    Ai = torch.randint(-8, 9, (M, K), device=DEV, generator=g).float()
+    Bi = torch.randint(-8, 9, (N, K), device=DEV, generator=g).float()
+    assert torch.equal(ops.gemm_nt(Ai, Bi).double(), Ai.double() @ Bi.double().T)
+    # fused affine epilogue and strided operands
+    alpha = torch.tensor([0.37], device=DEV)
+    bias = torch.randn(N, device=DEV, generator=g)
+    C2 = torch.empty(M, N, device=DEV)
+    wide = torch.zeros(M, K + 4, device=DEV)
+    wide[:, :K] = A
+    C1 = ops.gemm_nt(wide[:, :K], B, out2=C2, alpha=alpha, bias=bias)
+    assert float((C1.double() - ref).abs().max()) / scale < 3e-6
+    assert float((C2.double() - (0.37 * ref + bias.double())).abs().max()) / scale < 3e-6
+    w = torch.randn(M, device=DEV, generator=g)
+    assert torch.equal(ops.transpose_scale(A, w), (A * w[:, None]).T.contiguous())
+
+
 def test_cmaes_on_cuda_reproduces_reference_trajectory(golden):
     """The reference's CMA-ES run (its z draws recorded) through the CUDA searcher: GEMM sampling, K2 evaluation, K3 ranking,
     K4 weighted recombination, rank-mu SYRK and Cholesky must reproduce (m, sigma, C, A, paths)."""
