@@ -364,7 +364,8 @@ static GradPlan plan_grad(int64_t n_units, int64_t D, bool vec_ok) {
   p.n_coltiles = (int)((col_threads + p.tx - 1) / p.tx);
   const int ty = kGradThreads / p.tx;
   int64_t chunks = (int64_t)kNumSMs * EVOK_GRAD_CTAS_PER_SM / p.n_coltiles;  // one wave of resident CTAs
-  const int64_t max_useful = (n_units + (int64_t)ty * kGradUnroll - 1) / ((int64_t)ty * kGradUnroll);
+  // at least 16 unrolled iterations per CTA: fewer, fatter chunks keep the fixed-order finalisation short for small populations
+  const int64_t max_useful = (n_units + (int64_t)ty * kGradUnroll * 16 - 1) / ((int64_t)ty * kGradUnroll * 16);
   if (chunks > max_useful) chunks = max_useful;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;

@@ -389,10 +389,20 @@ class ExpGaussian(Distribution):
         return self.sigma.transpose(0, 1) @ self.sigma
 
     def to_global_coordinates(self, local_coordinates: torch.Tensor) -> torch.Tensor:
+        """mu + z A^T (distributions.py:928-938); the tcgen05 GEMM with the `+ mu` epilogue on CUDA fp32."""
+        if ops.uses_kernels(local_coordinates) and ops.uses_kernels(self.A) and local_coordinates.ndim == 2:
+            z = local_coordinates.contiguous()
+            out = torch.empty_like(z)
+            ops.gemm_nt(z, self.A.contiguous(), torch.empty_like(z), out2=out, bias=self.mu.contiguous())
+            return out
         return self.mu.unsqueeze(0) + (self.A @ local_coordinates.T).T
 
     def to_local_coordinates(self, global_coordinates: torch.Tensor) -> torch.Tensor:
-        return (self.A_inv @ (global_coordinates - self.mu.unsqueeze(0)).T).T
+        """(x - mu) A^-T (distributions.py:940-950)."""
+        centered = global_coordinates - self.mu.unsqueeze(0)
+        if ops.uses_kernels(centered) and ops.uses_kernels(self.A_inv) and centered.ndim == 2:
+            return ops.gemm_nt(centered.contiguous(), self.A_inv.contiguous())
+        return (self.A_inv @ centered.T).T
 
     def _fill(self, out: torch.Tensor, *, generator: Any = None):
         make_gaussian(out=out, generator=extract_generator(generator))
@@ -403,7 +413,12 @@ class ExpGaussian(Distribution):
         if ranking_used not in ("centered", "normalized"):
             weights = weights - torch.mean(weights)
         d_grad = torch.mv(z.T, weights)
-        m_grad = (z.T * weights) @ z - torch.sum(weights) * self.eye
+        if ops.uses_kernels(z) and ops.uses_kernels(weights):
+            zc = z.contiguous()
+            outer = ops.gemm_nt(ops.transpose_scale(zc, weights.contiguous()), ops.transpose_scale(zc))  # Z^T diag(w) Z
+        else:
+            outer = (z.T * weights) @ z
+        m_grad = outer - torch.sum(weights) * self.eye
         return {"d": d_grad, "M": m_grad}
 
     def update_parameters(self, gradients: dict, *, learning_rates: Optional[dict] = None, optimizers: Optional[dict] = None):

@@ -523,6 +523,29 @@ def test_cmaes_on_cuda_reproduces_reference_trajectory(golden):
     assert c2.status["mean_eval"] < 0.2 * m0
 
 
+def test_xnes_on_cuda_matches_reference_golden(golden):
+    from evotorch_b200.algorithms import XNES
+    from evotorch_b200.distributions import ExpGaussian
+
+    dist = ExpGaussian({"mu": C(golden["xnes/mu"]), "sigma": C(golden["xnes/A"]), "sigma_inv": C(golden["xnes/A_inv"])})
+    for method in ("nes", "centered"):
+        g = dist.compute_gradients(C(golden["xnes/X"]), C(golden["xnes/f"]), objective_sense="min", ranking_method=method)
+        close(N(g["d"]), golden[f"xnes/{method}/d"], rtol=1e-4, atol=3e-6)
+        close(N(g["M"]), golden[f"xnes/{method}/M"], rtol=1e-4, atol=6e-6)
+        upd = dist.update_parameters(g, learning_rates={"mu": 1.0, "sigma": 0.3})
+        close(N(upd.mu), golden[f"xnes/{method}/new_mu"], rtol=2e-5, atol=3e-6)
+        close(N(upd.A), golden[f"xnes/{method}/new_A"], rtol=2e-5, atol=3e-6)
+        close(N(upd.A_inv), golden[f"xnes/{method}/new_A_inv"], rtol=2e-5, atol=6e-6)
+    x = dist.sample(64, generator=torch.Generator(device=DEV).manual_seed(0))
+    close(N(dist.to_global_coordinates(dist.to_local_coordinates(x))), N(x), rtol=1e-4, atol=1e-4)
+    prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=12, device=DEV, seed=2)
+    s = XNES(prob, popsize=64, stdev_init=1.0)
+    s.step()
+    m0 = s.status["mean_eval"]
+    s.run(80)
+    assert s.status["mean_eval"] < 0.2 * m0
+
+
 # ---------------------------------------------------------------------------------------------- K8 batched policy forward
 def test_policy_kernel_matches_reference_golden_and_oracle(golden):
     from evotorch_b200.neuroevolution import Policy
