@@ -32,7 +32,7 @@ def summarise(rep, out, title):
         f.write(f"# {title}\n# source: {os.path.basename(rep)} (ncu --set full --clock-control none --import-source on)\n")
         f.write(f"# kernel: {vals[hdr.index('Kernel Name')]}\n")
         for i, h in enumerate(hdr):
-            if h in KEEP or ("issue_stalled" in h and "per_issue_active" in h):
+            if h in KEEP or ("issue_stalled" in h and "per_issue_active" in h) or (("pipe_tensor" in h or "pipe_tmem" in h) and ".avg" in h):
                 f.write(f"{h},{units[i]},{vals[i]}\n")
     print("wrote", out)
 
@@ -69,7 +69,8 @@ os.makedirs(P, exist_ok=True)
 for rep, name, title in (("prof_sample_eval", "ncu_sample_eval", "fused Philox sample + Rastrigin evaluate kernel (PGPE 200k x 10k)"),
                          ("prof_grad", "ncu_grad", "TMA-staged weighted column reduction kernel (PGPE 200k x 10k)"),
                          ("prof_scatter", "ncu_radix_scatter", "radix sort scatter pass (N = 1M keys)"),
-                         ("prof_mlp", "ncu_mlp_forward", "batched MLP policy forward (65536 x 100881)")):
+                         ("prof_mlp", "ncu_mlp_forward", "batched MLP policy forward (65536 x 100881)"),
+                         ("prof_gemm", "ncu_gemm_tf32x3", "tcgen05 3xTF32 GEMM, 4096 x 1024 x 1024 (CMA-ES Y = Z A^T)")):
     path = os.path.join(G, rep + ".ncu-rep")
     if os.path.exists(path):
         summarise(path, os.path.join(P, f"{TAG}_{name}.csv"), title)
