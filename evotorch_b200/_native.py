@@ -23,7 +23,7 @@ _SIGNATURES = {
     "evok_abi_version": (c_int, []),
     "evok_launch_count": (c_uint64, []),
     "evok_error_string": (ctypes.c_char_p, [c_int]),
-    "evok_sample_eval": (c_int, [c_int, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint64, _P, _P]),
+    "evok_sample_eval": (c_int, [c_int, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint64, _P, _P, _P]),
     "evok_eval": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P]),
     "evok_rank_workspace_bytes": (c_size_t, [c_int64]),
     "evok_rank": (c_int, [c_int, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
@@ -32,7 +32,7 @@ _SIGNATURES = {
     "evok_elite_mask": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "evok_grad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "evok_grad": (c_int, [c_int, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_float, c_float, _P, _P, _P, c_size_t, _P]),
-    "evok_grad_regen": (c_int, [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_float, c_float, _P, _P, _P,
+    "evok_grad_regen": (c_int, [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_uint64, c_uint64, _P, c_float, c_float, _P, _P, _P,
                                 c_size_t, _P]),
     "evok_clipup_step": (c_int, [_P, c_int64, _P, c_float, c_float, c_float, _P, _P, _P]),
     "evok_adam_step": (c_int, [_P, c_int64, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P, _P]),

@@ -13,6 +13,7 @@ For a CUDA float32 problem that is five kernel groups per generation and no host
 from __future__ import annotations
 
 import math
+import os
 from copy import deepcopy
 from typing import Optional
 
@@ -81,6 +82,8 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         self._mean_eval = None
         self._population: Optional[SolutionBatch] = None
         self._first_iter = True
+        self._use_graph = os.environ.get("EVOTORCH_B200_CUDA_GRAPH", "0") == "1"
+        self._graph = None
         SinglePopulationAlgorithmMixin.__init__(self, exclude="mean_eval", enable=(not self._distributed))
 
     def _initialize_optimizer(self, learning_rate: float, optimizer=None, optimizer_config: Optional[dict] = None):
@@ -98,12 +101,84 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             self._population = SolutionBatch(self.problem, popsize=self._popsize, device=self._distribution.device, empty=True)
         self.problem.sample_and_evaluate(self._distribution, self._population)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of a whole generation
+    def enable_cuda_graph(self, enabled: bool = True):
+        """Capture one generation (rank -> gradients -> update -> fused sample/evaluate) into a CUDA graph and replay it from
+        `step()`: one graph launch instead of ~20 kernel launches and their Python glue.  The trajectory is bit-identical to
+        the eager path: the sampler reads a device-side generation counter that an in-graph kernel increments.  Falls back to
+        eager stepping whenever the configuration is not capturable (see `_graph_capturable`)."""
+        self._use_graph = bool(enabled)
+        self._graph = None
+        return self
+
+    def _graph_capturable(self) -> bool:
+        from ..optimizers import ClipUp
+
+        dist, prob = self._distribution, self.problem
+        return (isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
+                and prob.evok_objective_id is not None and len(prob.senses) == 1 and (self._optimizer is None or isinstance(self._optimizer, ClipUp))
+                and self._population is not None and self._population._evdata.shape[1] == 1 and not self._distributed)
+
+    def _update_in_place(self, gradients: dict):
+        """Same arithmetic as `_update_distribution` on CUDA, but writing into the live mu / sigma buffers (replayable)."""
+        dist = self._distribution
+        gmu = gradients["mu"].contiguous()
+        if self._optimizer is not None:
+            self._optimizer.ascent_into_(gmu, dist.mu)
+        else:
+            ops.axpy_(dist.mu, gmu, self._center_learning_rate)
+        ops.sigma_update_(dist.sigma, gradients["sigma"].contiguous(), self._stdev_learning_rate, isinstance(dist, ExpSeparableGaussian),
+                          lb=self._stdev_min, ub=self._stdev_max, max_change=self._stdev_max_change)
+
+    def _graph_body(self, base_stream: int, counter: torch.Tensor):
+        dist, prob, pop = self._distribution, self.problem, self._population
+        samples = pop._data
+        fitnesses = pop._evdata.view(-1)
+        gradients = dist.compute_gradients(samples, fitnesses, objective_sense=prob.senses[self._obj_index], ranking_method=self._ranking_method)
+        self._update_in_place(gradients)
+        ops.sample_eval(prob.evok_objective_id, samples, dist.mu, dist.sigma, n_rows=samples.shape[0], symmetric=dist.SYMMETRIC,
+                        seed=prob._philox_seed, stream_id=base_stream, f=fitnesses, stream_offset=counter)
+        counter.add_(1)
+
+    def _capture_graph(self):
+        prob = self.problem
+        # the distribution's tensors become the persistent, in-place-updated buffers of the graph
+        dist = self._distribution
+        if not (dist.mu.is_contiguous() and dist.sigma.is_contiguous()):
+            self._distribution = dist = dist.modified_copy(mu=dist.mu.contiguous(), sigma=dist.sigma.contiguous())
+        self._graph_counter = torch.zeros(1, dtype=torch.int32, device=dist.mu.device)
+        self._graph_base_stream = prob._philox_stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._graph_body(self._graph_base_stream, self._graph_counter)
+        self._graph_counter.zero_()
+        self._graph = graph
+
+    def _step_graph(self):
+        prob, pop = self.problem, self._population
+        if self._graph is None:
+            # one more eager generation right before the capture: warms every kernel and workspace that the graph will use
+            self._step_eager()
+            self._capture_graph()
+            return
+        prob._before_eval_hook(pop)
+        self._graph.replay()
+        prob._philox_stream += 1  # keep the host-side stream counter in step with the device-side one
+        prob._finish_evaluation(pop)
+
     def _step_non_distributed(self):
         """gaussian.py:274-367."""
         if self._first_iter:
             self._fill_and_eval_pop()
             self._first_iter = False
             return
+        if self._use_graph and self._graph_capturable():
+            self._step_graph()
+        else:
+            self._graph = None
+            self._step_eager()
+
+    def _step_eager(self):
         samples = self._population.access_values(keep_evals=True)
         fitnesses = self._population.access_evals()[:, self._obj_index]
         gradients = self._distribution.compute_gradients(samples, fitnesses, objective_sense=self.problem.senses[self._obj_index],
@@ -157,10 +232,12 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
 
     # ------------------------------------------------------------------ status
     def _get_mu(self) -> torch.Tensor:
-        return self._distribution.parameters["mu"]
+        mu = self._distribution.parameters["mu"]
+        return mu.clone() if self._graph is not None else mu  # graph replays update the live buffer in place
 
     def _get_sigma(self) -> torch.Tensor:
-        return self._distribution.parameters["sigma"]
+        sigma = self._distribution.parameters["sigma"]
+        return sigma.clone() if self._graph is not None else sigma
 
     def _get_mean_eval(self) -> Optional[float]:
         if self._population is None:

@@ -93,12 +93,14 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 
 // The four standard normals of (unit, column group q): `unit` is the GLOBAL direction index (symmetric
 // sampling: rows 2*unit and 2*unit+1) or the global row index (non-symmetric); columns 4q .. 4q+3.
-__device__ __forceinline__ void normals4(const PhiloxKey& key, uint64_t unit, uint32_t q, float z[4]) {
+// `stream_word` = low 32 bits of the stream id (key.stream_lo plus an optional device-side generation offset, which lets a
+// CUDA graph that was captured once draw a fresh population on every replay)
+__device__ __forceinline__ void normals4(const PhiloxKey& key, uint32_t stream_word, uint64_t unit, uint32_t q, float z[4]) {
   U4 c;
   c.x = q;
   c.y = (uint32_t)unit;
   c.z = (uint32_t)(unit >> 32);
-  c.w = key.stream_lo;
+  c.w = stream_word;
   const U4 r = philox4x32_10(c, key);
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);

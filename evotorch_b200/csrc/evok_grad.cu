@@ -55,8 +55,9 @@ template <int VEC, int TX, bool SYM, bool REGEN>
 __global__ void __launch_bounds__(kGradThreads, EVOK_GRAD_MINB)
     grad_partial_kernel(int form, const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, const float* __restrict__ mu,
                         const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk, uint64_t unit0,
-                        const __grid_constant__ PhiloxKey key, float* __restrict__ partial) {
+                        const __grid_constant__ PhiloxKey key, const uint32_t* __restrict__ stream_off, float* __restrict__ partial) {
   constexpr int TY = kGradThreads / TX;
+  const uint32_t sw = key.stream_lo + ((REGEN && stream_off) ? __ldg(stream_off) : 0u);
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int64_t col = ((int64_t)blockIdx.x * TX + tx) * VEC;
   const bool active = col < D;
@@ -112,10 +113,10 @@ __global__ void __launch_bounds__(kGradThreads, EVOK_GRAD_MINB)
       if (need[u]) {
         if (REGEN) {
           if (VEC == 4) {
-            normals4(key, unit0 + (uint64_t)r, (uint32_t)(col >> 2), x[u].v);
+            normals4(key, sw, unit0 + (uint64_t)r, (uint32_t)(col >> 2), x[u].v);
           } else {
             float z[4];
-            normals4(key, unit0 + (uint64_t)r, (uint32_t)(col >> 2), z);
+            normals4(key, sw, unit0 + (uint64_t)r, (uint32_t)(col >> 2), z);
             x[u].v[0] = z[col & 3];
           }
         } else {
@@ -377,12 +378,13 @@ static GradPlan plan_grad(int64_t n_units, int64_t D, bool vec_ok) {
 
 template <int VEC, bool SYM, bool REGEN>
 static void launch_partial(const GradPlan& p, int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma,
-                           int64_t n_units, int64_t D, uint64_t unit0, uint64_t seed, uint64_t stream_id, float* partial, cudaStream_t st) {
+                           int64_t n_units, int64_t D, uint64_t unit0, uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float* partial,
+                           cudaStream_t st) {
   dim3 grid(p.n_coltiles, p.n_chunks);
   const PhiloxKey key = make_philox_key(seed, stream_id);
 #define EVOK_LAUNCH_TX(TXV)                                                                                                         \
   grad_partial_kernel<VEC, TXV, SYM, REGEN><<<grid, kGradThreads, 0, st>>>(form, X, ldx, w, mu, sigma, n_units, D, p.units_per_chunk, \
-                                                                           unit0, key, partial)
+                                                                           unit0, key, stream_off, partial)
   switch (p.tx) {
     case 32: EVOK_LAUNCH_TX(32); break;
     case 64: EVOK_LAUNCH_TX(64); break;
@@ -393,7 +395,7 @@ static void launch_partial(const GradPlan& p, int form, const float* X, int64_t 
 }
 
 static int grad_impl(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
-                     int64_t D, bool regen, uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu,
+                     int64_t D, bool regen, uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float scale_mu, float scale_sigma, float* out_mu,
                      float* out_sigma, void* ws, size_t ws_bytes, void* stream) {
   if (!w || !mu || !sigma || !out_mu || !out_sigma || !ws || (!regen && !X)) return EVOK_E_NULLPTR;
   if (form < EVOK_GRAD_SEPARABLE || form > EVOK_GRAD_MOMENTS) return EVOK_E_BADENUM;
@@ -438,14 +440,14 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
     return 0;
   }
   if (regen) {
-    if (sym) launch_partial<4, true, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
-    else launch_partial<4, false, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    if (sym) launch_partial<4, true, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
+    else launch_partial<4, false, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
   } else if (vec_ok) {
-    if (sym) launch_partial<4, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
-    else launch_partial<4, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    if (sym) launch_partial<4, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
+    else launch_partial<4, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
   } else {
-    if (sym) launch_partial<1, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
-    else launch_partial<1, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, partial, st);
+    if (sym) launch_partial<1, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
+    else launch_partial<1, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
   }
   EVOK_CHECK_LAUNCH();
   grad_finalize_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(partial, p.n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
@@ -467,12 +469,12 @@ extern "C" EVOK_API size_t evok_grad_workspace_bytes(int64_t n_rows, int64_t D) 
 extern "C" EVOK_API int evok_grad(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t n_rows,
                          int64_t D, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma, void* ws, size_t ws_bytes,
                          void* stream) {
-  return grad_impl(form, X, ldx, w, mu, sigma, 0, n_rows, D, false, 0, 0, scale_mu, scale_sigma, out_mu, out_sigma, ws, ws_bytes, stream);
+  return grad_impl(form, X, ldx, w, mu, sigma, 0, n_rows, D, false, 0, 0, nullptr, scale_mu, scale_sigma, out_mu, out_sigma, ws, ws_bytes, stream);
 }
 
 extern "C" EVOK_API int evok_grad_regen(int form, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
-                               uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma,
-                               void* ws, size_t ws_bytes, void* stream) {
-  return grad_impl(form, nullptr, 0, w, mu, sigma, row0, n_rows, D, true, seed, stream_id, scale_mu, scale_sigma, out_mu, out_sigma, ws,
+                               uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, float scale_mu, float scale_sigma,
+                               float* out_mu, float* out_sigma, void* ws, size_t ws_bytes, void* stream) {
+  return grad_impl(form, nullptr, 0, w, mu, sigma, row0, n_rows, D, true, seed, stream_id, stream_offset_dev, scale_mu, scale_sigma, out_mu, out_sigma, ws,
                    ws_bytes, stream);
 }

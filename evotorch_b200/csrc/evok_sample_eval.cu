@@ -45,11 +45,11 @@ struct SampleTune {
 
 // one column group (4 columns) of one unit: sample, store, accumulate
 template <int OBJ, bool SYM, bool STORE, bool VEC>
-__device__ __forceinline__ void sample_group(const PhiloxKey& key, uint64_t unit, uint32_t q, int64_t D,
+__device__ __forceinline__ void sample_group(const PhiloxKey& key, uint32_t sw, uint64_t unit, uint32_t q, int64_t D,
                                              const float* __restrict__ mu, const float* __restrict__ sigma, float* xp, float* xm,
                                              ObjAcc<OBJ>& accp, ObjAcc<OBJ>& accm) {
   float z[4];
-  normals4(key, unit, q, z);
+  normals4(key, sw, unit, q, z);
   const int64_t j = (int64_t)q << 2;
   if (VEC) {
     const float4 m = __ldg(reinterpret_cast<const float4*>(mu + j));
@@ -83,8 +83,10 @@ __device__ __forceinline__ void sample_group(const PhiloxKey& key, uint64_t unit
 template <int OBJ, bool SYM, bool STORE, bool VEC>
 __global__ void __launch_bounds__(kSampleThreads, SampleTune<OBJ>::kMinBlocks)
     sample_eval_kernel(float* __restrict__ X, int64_t ldx, const float* __restrict__ mu, const float* __restrict__ sigma,
-                       int64_t row0, int64_t n_units, int64_t D, const __grid_constant__ PhiloxKey key, float* __restrict__ f) {
+                       int64_t row0, int64_t n_units, int64_t D, const __grid_constant__ PhiloxKey key, const uint32_t* __restrict__ stream_off,
+                       float* __restrict__ f) {
   const int lane = threadIdx.x & 31;
+  const uint32_t sw = key.stream_lo + (stream_off ? __ldg(stream_off) : 0u);
   const int64_t warps_total = (int64_t)gridDim.x * (kSampleThreads / 32);
   const int64_t gw = (int64_t)blockIdx.x * (kSampleThreads / 32) + (threadIdx.x >> 5);
   const uint32_t nq = (uint32_t)((D + 3) >> 2);
@@ -103,10 +105,10 @@ __global__ void __launch_bounds__(kSampleThreads, SampleTune<OBJ>::kMinBlocks)
       for (; q + 32u * (kSampleUnroll - 1) < nq; q += 32u * kSampleUnroll) {
 #pragma unroll
         for (int uu = 0; uu < kSampleUnroll; ++uu)
-          sample_group<OBJ, SYM, STORE, VEC>(key, unit, q + 32u * uu, D, mu, sigma, xp, xm, accp, accm);
+          sample_group<OBJ, SYM, STORE, VEC>(key, sw, unit, q + 32u * uu, D, mu, sigma, xp, xm, accp, accm);
       }
     }
-    for (; q < nq; q += 32) sample_group<OBJ, SYM, STORE, VEC>(key, unit, q, D, mu, sigma, xp, xm, accp, accm);
+    for (; q < nq; q += 32) sample_group<OBJ, SYM, STORE, VEC>(key, sw, unit, q, D, mu, sigma, xp, xm, accp, accm);
     if (OBJ != EVOK_OBJ_NONE) {
       const float fp = accp.finish(D);
       float fm = 0.f;
@@ -166,17 +168,17 @@ static int resident_grid(K kernel, int threads, int64_t units_per_cta_needed) {
 
 template <int OBJ, bool SYM, bool STORE>
 static int launch_sample(float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
-                         uint64_t seed, uint64_t stream_id, float* f, cudaStream_t st) {
+                         uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float* f, cudaStream_t st) {
   const int64_t n_units = SYM ? n_rows / 2 : n_rows;
   const bool vec = (D % 4 == 0) && aligned16(mu) && aligned16(sigma) && (!STORE || (aligned16(X) && ldx % 4 == 0));
   const int64_t ctas_needed = (n_units + (kSampleThreads / 32) - 1) / (kSampleThreads / 32);
   const PhiloxKey key = make_philox_key(seed, stream_id);
   if (vec) {
     auto k = sample_eval_kernel<OBJ, SYM, STORE, true>;
-    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, f);
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, stream_off, f);
   } else {
     auto k = sample_eval_kernel<OBJ, SYM, STORE, false>;
-    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, f);
+    k<<<resident_grid(k, kSampleThreads, ctas_needed), kSampleThreads, 0, st>>>(X, ldx, mu, sigma, row0, n_units, D, key, stream_off, f);
   }
   EVOK_CHECK_LAUNCH();
   return 0;
@@ -184,13 +186,13 @@ static int launch_sample(float* X, int64_t ldx, const float* mu, const float* si
 
 template <int OBJ>
 static int dispatch_sample(float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0, int64_t n_rows, int64_t D,
-                           int symmetric, uint64_t seed, uint64_t stream_id, float* f, cudaStream_t st) {
+                           int symmetric, uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float* f, cudaStream_t st) {
   if (symmetric) {
-    return X ? launch_sample<OBJ, true, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st)
-             : launch_sample<OBJ, true, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st);
+    return X ? launch_sample<OBJ, true, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, stream_off, f, st)
+             : launch_sample<OBJ, true, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, stream_off, f, st);
   }
-  return X ? launch_sample<OBJ, false, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st)
-           : launch_sample<OBJ, false, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, f, st);
+  return X ? launch_sample<OBJ, false, true>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, stream_off, f, st)
+           : launch_sample<OBJ, false, false>(X, ldx, mu, sigma, row0, n_rows, D, seed, stream_id, stream_off, f, st);
 }
 
 template <int OBJ>
@@ -213,8 +215,9 @@ static int launch_eval(const float* X, int64_t ldx, int64_t n_rows, int64_t D, f
 using namespace evok;
 
 extern "C" EVOK_API int evok_sample_eval(int objective, float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0,
-                                int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, float* f,
-                                void* stream) {
+                                int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id,
+                                const uint32_t* stream_offset_dev, float* f, void* stream) {
+  const uint32_t* stream_off = stream_offset_dev;
   if (!mu || !sigma) return EVOK_E_NULLPTR;
   if (objective < 0 || objective >= EVOK_OBJ_COUNT) return EVOK_E_BADENUM;
   if (objective == EVOK_OBJ_NONE && !X) return EVOK_E_NULLPTR;
@@ -224,10 +227,10 @@ extern "C" EVOK_API int evok_sample_eval(int objective, float* X, int64_t ldx, c
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (objective) {
-    case EVOK_OBJ_NONE: return dispatch_sample<EVOK_OBJ_NONE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
-    case EVOK_OBJ_SPHERE: return dispatch_sample<EVOK_OBJ_SPHERE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
-    case EVOK_OBJ_RASTRIGIN: return dispatch_sample<EVOK_OBJ_RASTRIGIN>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
-    case EVOK_OBJ_ACKLEY: return dispatch_sample<EVOK_OBJ_ACKLEY>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, f, st);
+    case EVOK_OBJ_NONE: return dispatch_sample<EVOK_OBJ_NONE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, stream_off, f, st);
+    case EVOK_OBJ_SPHERE: return dispatch_sample<EVOK_OBJ_SPHERE>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, stream_off, f, st);
+    case EVOK_OBJ_RASTRIGIN: return dispatch_sample<EVOK_OBJ_RASTRIGIN>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, stream_off, f, st);
+    case EVOK_OBJ_ACKLEY: return dispatch_sample<EVOK_OBJ_ACKLEY>(X, ldx, mu, sigma, row0, n_rows, D, symmetric, seed, stream_id, stream_off, f, st);
   }
   return EVOK_E_BADENUM;
 }

@@ -91,8 +91,17 @@ def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ K1 / K2
+def _offset_ptr(stream_offset: Optional[torch.Tensor]) -> Optional[int]:
+    if stream_offset is None:
+        return None
+    if not (stream_offset.is_cuda and stream_offset.dtype == torch.int32 and stream_offset.numel() >= 1):
+        raise ValueError("stream_offset: expected an int32 CUDA tensor with one element")
+    return stream_offset.data_ptr()
+
+
 def sample_eval(objective: int, X: Optional[torch.Tensor], mu: torch.Tensor, sigma: torch.Tensor, *, n_rows: int, symmetric: bool,
-                seed: int, stream_id: int, row0: int = 0, f: Optional[torch.Tensor] = None) -> None:
+                seed: int, stream_id: int, row0: int = 0, f: Optional[torch.Tensor] = None,
+                stream_offset: Optional[torch.Tensor] = None) -> None:
     D = mu.numel()
     _vec(mu, "mu"); _vec(sigma, "sigma", D)
     ldx = 0
@@ -111,7 +120,8 @@ def sample_eval(objective: int, X: Optional[torch.Tensor], mu: torch.Tensor, sig
         return
     with _timed("sample_eval" if objective != OBJ_NONE else "sample"):
         rc = nat.lib().evok_sample_eval(objective, nat.ptr(X), ldx, mu.data_ptr(), sigma.data_ptr(), row0, n_rows, D, int(symmetric),
-                                        seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, nat.ptr(f), nat.stream_of(mu))
+                                        seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, _offset_ptr(stream_offset), nat.ptr(f),
+                                        nat.stream_of(mu))
     nat.check(rc, "evok_sample_eval")
 
 
@@ -192,7 +202,7 @@ def grad(form: int, X: torch.Tensor, w: torch.Tensor, mu: torch.Tensor, sigma: t
 
 def grad_regen(form: int, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, *, seed: int, stream_id: int, row0: int,
                scale_mu: float, scale_sigma: float, out_mu: Optional[torch.Tensor] = None,
-               out_sigma: Optional[torch.Tensor] = None) -> tuple:
+               out_sigma: Optional[torch.Tensor] = None, stream_offset: Optional[torch.Tensor] = None) -> tuple:
     n, D = w.numel(), mu.numel()
     _vec(w, "weights"); _vec(mu, "mu"); _vec(sigma, "sigma", D)
     out_mu = torch.empty_like(mu) if out_mu is None else _vec(out_mu, "out_mu", D)
@@ -200,8 +210,8 @@ def grad_regen(form: int, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor
     ws = nat.workspace(mu.device, nat.lib().evok_grad_workspace_bytes(n, D), "grad")
     with _timed("grad_regen"):
         rc = nat.lib().evok_grad_regen(form, w.data_ptr(), mu.data_ptr(), sigma.data_ptr(), row0, n, D, seed & 0xFFFFFFFFFFFFFFFF,
-                                       stream_id & 0xFFFFFFFFFFFFFFFF, scale_mu, scale_sigma, out_mu.data_ptr(), out_sigma.data_ptr(),
-                                       ws.data_ptr(), ws.numel(), nat.stream_of(mu))
+                                       stream_id & 0xFFFFFFFFFFFFFFFF, _offset_ptr(stream_offset), scale_mu, scale_sigma, out_mu.data_ptr(),
+                                       out_sigma.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(mu))
     nat.check(rc, "evok_grad_regen")
     return out_mu, out_sigma
 

@@ -78,10 +78,13 @@ const char* evok_error_string(int code);
  * symmetric != 0: rows 2k and 2k+1 are mu + sigma*z_k and mu - sigma*z_k (row0 and n_rows even).
  * X may be NULL when objective != NONE ("lazy population": evaluate without materialising).
  * f may be NULL when objective == NONE.
- * --------------------------------------------------------------------------------------------- */
+ * stream_offset_dev (nullable): device pointer to a 32-bit generation counter that is ADDED to the low word of
+ * stream_id when the kernel runs -- a CUDA graph captured once then draws a fresh population at every replay
+ * (the host increments the counter with an in-graph kernel); NULL = use stream_id as is.
+ */
 int evok_sample_eval(int objective, float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0,
-                     int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, float* f,
-                     void* stream);
+                     int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id,
+                     const uint32_t* stream_offset_dev, float* f, void* stream);
 
 /* K2 alone: f[i] = objective(X[i, :]) for an already materialised population (torch-RNG parity mode,
  * CMA-ES / XNES populations).  Replaces the user's vectorised torch objective at core.py:2604. */
@@ -131,8 +134,8 @@ int evok_grad(int form, const float* X, int64_t ldx, const float* w, const float
 /* K4 without a materialised population: regenerates eps from the Philox counters used by
  * evok_sample_eval(..., X = NULL) with the same (seed, stream_id, row0). */
 int evok_grad_regen(int form, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
-                    int64_t D, uint64_t seed, uint64_t stream_id, float scale_mu, float scale_sigma, float* out_mu,
-                    float* out_sigma, void* ws, size_t ws_bytes, void* stream);
+                    int64_t D, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, float scale_mu,
+                    float scale_sigma, float* out_mu, float* out_sigma, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5: D-vector updates (no host synchronisation; norms are reduced on the device).

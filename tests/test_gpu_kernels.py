@@ -445,6 +445,42 @@ def test_cuda_searchers_optimise_and_are_seed_deterministic(algo):
     assert math.isfinite(a.status["pop_best_eval"]) and a.status["pop_best"].values.shape == (200,)
 
 
+@pytest.mark.parametrize("algo", ["pgpe", "pgpe_plain_nonsym", "snes", "cem"])
+def test_cuda_graph_replay_is_bit_identical_to_eager(algo):
+    def make():
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=300, device=DEV, seed=21)
+        if algo == "pgpe":
+            return PGPE(prob, popsize=1000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+        if algo == "pgpe_plain_nonsym":
+            return PGPE(prob, popsize=1000, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0, symmetric=False, optimizer=None,
+                        ranking_method="nes", stdev_min=0.01, stdev_max=3.0)
+        if algo == "snes":
+            return SNES(prob, popsize=1000, stdev_init=2.0)
+        return CEM(prob, popsize=1000, parenthood_ratio=0.25, stdev_init=2.0, stdev_max_change=0.5)
+
+    eager, graph = make(), make().enable_cuda_graph()
+    seen = []
+    graph.after_step_hook.append(lambda: seen.append(1) or {})
+    for gen in range(12):
+        eager.step()
+        graph.step()
+        assert torch.equal(eager.status["center"], graph.status["center"]), gen
+        assert torch.equal(eager.status["stdev"], graph.status["stdev"]), gen
+        assert torch.equal(eager.population.values, graph.population.values), gen
+        assert torch.equal(eager.population.evals, graph.population.evals), gen
+    assert graph._graph is not None and len(seen) == 12
+    assert graph.status["mean_eval"] == eager.status["mean_eval"]
+    # status tensors read in graph mode are snapshots, not views of the live buffers
+    c = graph.status["center"]
+    graph.step()
+    assert not torch.equal(c, graph.status["center"])
+    # an Adam-driven searcher is not capturable (host-side bias correction) and silently keeps stepping eagerly
+    prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=64, device=DEV, seed=3)
+    adam = PGPE(prob, popsize=200, center_learning_rate=0.05, stdev_learning_rate=0.1, stdev_init=1.0, optimizer="adam").enable_cuda_graph()
+    adam.run(4)
+    assert adam._graph is None and adam.step_count == 4
+
+
 def test_user_objective_and_torch_rng_paths_on_cuda():
     def my_sphere(x):
         return torch.sum(x * x, dim=-1)

@@ -40,7 +40,7 @@ def test_host_side_argument_checks_need_no_gpu(libpath):
     lib = nat.lib()
     assert lib.evok_rank_workspace_bytes(1_000_000) >= 16_000_000
     assert lib.evok_grad_workspace_bytes(1000, 10_000) > 0
-    assert lib.evok_sample_eval(2, None, 0, None, None, 0, 4, 4, 1, 0, 0, None, None) == -1  # null pointers
+    assert lib.evok_sample_eval(2, None, 0, None, None, 0, 4, 4, 1, 0, 0, None, None, None) == -1  # null pointers
     assert lib.evok_rank(9, 1, 4, 0, 1, None, 1, 0, None) == -3  # bad enum (pointers are never dereferenced on the host)
     assert lib.evok_clipup_step(None, 4, None, 0.1, 0.9, 0.2, None, None, None) == -1
 
