@@ -71,6 +71,11 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         self._stdev_min = bound(stdev_min, "stdev_min")
         self._stdev_max = bound(stdev_max, "stdev_max")
         self._stdev_max_change = bound(stdev_max_change, "stdev_max_change")
+
+        def host_side(x):  # scalar bounds as python floats (read once here: no device->host sync per generation)
+            return None if x is None else (float(x) if x.ndim == 0 else x)
+
+        self._kernel_bounds = dict(lb=host_side(self._stdev_min), ub=host_side(self._stdev_max), max_change=host_side(self._stdev_max_change))
         self._obj_index = problem.normalize_obj_index(obj_index)
 
         # `distributed=True` shards the population over torch.distributed ranks (the reference needs Ray actors for this)
@@ -128,7 +133,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         else:
             ops.axpy_(dist.mu, gmu, self._center_learning_rate)
         ops.sigma_update_(dist.sigma, gradients["sigma"].contiguous(), self._stdev_learning_rate, isinstance(dist, ExpSeparableGaussian),
-                          lb=self._stdev_min, ub=self._stdev_max, max_change=self._stdev_max_change)
+                          **self._kernel_bounds)
 
     def _graph_body(self, base_stream: int, counter: torch.Tensor):
         dist, prob, pop = self._distribution, self.problem, self._population
@@ -211,8 +216,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             else:
                 ops.axpy_(new_mu, gmu, self._center_learning_rate)
             ops.sigma_update_(new_sigma, gradients["sigma"].contiguous(), self._stdev_learning_rate,
-                              isinstance(dist, ExpSeparableGaussian), lb=self._stdev_min, ub=self._stdev_max,
-                              max_change=self._stdev_max_change)
+                              isinstance(dist, ExpSeparableGaussian), **self._kernel_bounds)
             self._distribution = dist.modified_copy(mu=new_mu, sigma=new_sigma)
             return
 
