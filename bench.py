@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-popsize", type=int, default=2_000, help="population rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=-1, help="1/0: replay each generation from a CUDA graph (default: on for N > 1)")
     return ap.parse_args()
 
 
@@ -189,6 +190,9 @@ def run_ours(args):
     problem = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=dev, seed=SEED)
     searcher = PGPE(problem, popsize=N, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT,
                     distributed=(world > 1))
+    use_graph = (world > 1) if args.cuda_graph < 0 else bool(args.cuda_graph)
+    if use_graph:
+        searcher.enable_cuda_graph()
     for _ in range(max(W, 3)):
         searcher.step()
 
@@ -291,7 +295,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": elapsed_ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world), "impl": "ours",
+        "config": dict(workload_config(args, world), cuda_graph=bool(use_graph)), "impl": "ours",
         "gpu_launches": int(launches), "clocks": clock_info, "e2e": e2e, "roofline": roofline, "kernels": kern,
         "whole_generation": {"model_bytes_per_gen_per_gpu": model_bytes, "model_gbs": model_bytes * value / 1e9,
                              "model_frac_of_peak": model_bytes * value / 1e9 / peak,

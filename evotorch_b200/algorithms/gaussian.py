@@ -120,9 +120,12 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         from ..optimizers import ClipUp
 
         dist, prob = self._distribution, self.problem
-        return (isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
-                and prob.evok_objective_id is not None and len(prob.senses) == 1 and (self._optimizer is None or isinstance(self._optimizer, ClipUp))
-                and self._population is not None and self._population._evdata.shape[1] == 1 and not self._distributed)
+        ok = (isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
+              and prob.evok_objective_id is not None and len(prob.senses) == 1 and prob.eval_data_length == 0
+              and (self._optimizer is None or isinstance(self._optimizer, ClipUp)))
+        if self._distributed:  # the sharded generation has no Python between its kernels / collectives either
+            return ok and not prob.stores_solution_stats and len(prob.before_eval_hook) == 0 and len(prob.after_eval_hook) == 0
+        return ok and self._population is not None
 
     def _update_in_place(self, gradients: dict):
         """Same arithmetic as `_update_distribution` on CUDA, but writing into the live mu / sigma buffers (replayable)."""
@@ -191,14 +194,43 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         self._update_distribution(gradients)
         self._fill_and_eval_pop()
 
-    def _step_distributed(self):
-        """Every rank: sample/evaluate its shard, global ranking, all-reduced gradients, replicated update
-        (replaces gaussian.py:199-272)."""
+    def _distributed_body(self, in_place: bool):
         fetched = self.problem.sample_and_compute_gradients(self._distribution, self._popsize, obj_index=self._obj_index,
                                                             ranking_method=self._ranking_method,
                                                             ensure_even_popsize=self._ensure_even_popsize)
-        self._update_distribution(fetched[0]["gradients"])
+        if in_place:
+            self._update_in_place(fetched[0]["gradients"])
+        else:
+            self._update_distribution(fetched[0]["gradients"])
         self._mean_eval = fetched[0]["mean_eval"]
+
+    def _step_distributed(self):
+        """Every rank: sample/evaluate its shard, global ranking, all-reduced gradients, replicated update
+        (replaces gaussian.py:199-272).  With `enable_cuda_graph()` the whole sequence, NCCL collectives included, is captured
+        once and replayed."""
+        prob = self.problem
+        if not (self._use_graph and self._graph_capturable()):
+            self._graph = None
+            self._distributed_body(in_place=False)
+            return
+        if self._graph is None:
+            if self._steps_count < 2:  # eager generations first: seed broadcast, NCCL communicators, workspaces, kernel warm-up
+                self._distributed_body(in_place=False)
+                return
+            dist = self._distribution
+            self._distribution = dist = dist.modified_copy(mu=dist.mu.contiguous().clone(), sigma=dist.sigma.contiguous().clone())
+            prob.philox_stream_offset = torch.zeros(1, dtype=torch.int32, device=dist.mu.device)
+            base = prob._philox_stream
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._distributed_body(in_place=True)
+                prob.philox_stream_offset.add_(1)
+            prob._philox_stream = base  # the capture consumed one host-side stream id without running anything
+            prob.philox_stream_offset.zero_()
+            self._graph = graph
+        self._graph.replay()
+        prob._philox_stream += 1
 
     # ------------------------------------------------------------------ distribution update (K5)
     def _update_distribution(self, gradients: dict):

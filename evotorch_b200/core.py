@@ -142,6 +142,7 @@ class Problem:
         self._philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._philox_stream = 0
         self.philox_row0 = 0  # global index of the first local row when the population is sharded over ranks
+        self.philox_stream_offset = None  # optional device-side generation counter (set while a CUDA graph is captured / replayed)
 
     def next_philox_stream(self) -> tuple:
         """(seed, stream_id) for the next kernel-sampled population; every call uses a fresh Philox stream."""
@@ -443,7 +444,8 @@ class Problem:
         direct = evdata.shape[1] == 1 and evdata.dtype == torch.float32 and evdata.is_contiguous()
         f = evdata.view(-1) if direct else torch.empty(n, dtype=torch.float32, device=values.device)
         ops.sample_eval(obj, values, distribution.mu.contiguous(), distribution.sigma.contiguous(), n_rows=n,
-                        symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id, row0=self.philox_row0, f=f)
+                        symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id, row0=self.philox_row0, f=f,
+                        stream_offset=self.philox_stream_offset)
         if not direct:
             batch.set_evals(f)
         self._finish_evaluation(batch)

@@ -87,5 +87,33 @@ gb = 4.0 * NP * pol.parameter_length / 1e9
 out["cfg4_policy_forward"] = {"ms": ms, "forwards_per_s": 1e3 / ms, "gbs": gb / ms * 1e3, "policies": NP, "params": pol.parameter_length,
                               "observations_per_policy": 1, "activation": "tanh"}
 print(json.dumps(out["cfg4_policy_forward"], indent=1), flush=True)
+# ---- small / medium problems: eager stepping vs CUDA-graph replay (launch-bound regime)
+from evotorch_b200.algorithms import PGPE, SNES  # noqa: E402
+from evotorch_b200.objectives import rastrigin  # noqa: E402
+
+
+def gens_per_s(make, graph, K=300):
+    s = make()
+    if graph:
+        s.enable_cuda_graph()
+    s.run(10)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s.run(K)
+    torch.cuda.synchronize()
+    return K / (time.perf_counter() - t0)
+
+
+small = {}
+for tag, make in (("snes_cfg1_shape_N1000_D100", lambda: SNES(Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=100, device=dev, seed=1),
+                                                              popsize=1000, stdev_init=10.0)),
+                  ("pgpe_N10000_D1000", lambda: PGPE(Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=1000, device=dev, seed=1),
+                                                     popsize=10000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)),
+                  ("pgpe_N100000_D10000_cfg2", lambda: PGPE(Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=10000, device=dev, seed=1),
+                                                            popsize=100000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0))):
+    small[tag] = {"eager_gen_per_s": gens_per_s(make, False), "cuda_graph_gen_per_s": gens_per_s(make, True)}
+    print(tag, small[tag], flush=True)
+out["eager_vs_cuda_graph"] = small
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)

@@ -50,6 +50,18 @@ for kind in ("pgpe", "snes", "cem"):
     ref = sharded.status["center"].clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, sharded.status["center"]), "ranks diverged"
+# CUDA-graph replay of the sharded generation (collectives captured) must equal the eager sharded run bit for bit
+for kind in ("pgpe", "snes"):
+    eager, graphed = make(kind, True), make(kind, True).enable_cuda_graph()
+    same = True
+    for gen in range(8):
+        eager.step()
+        graphed.step()
+        same = same and torch.equal(eager.status["center"], graphed.status["center"]) and torch.equal(eager.status["stdev"], graphed.status["stdev"])
+    good = same and graphed._graph is not None and abs(eager.status["mean_eval"] - graphed.status["mean_eval"]) < 1e-3
+    ok = ok and good
+    if rank == 0:
+        print(f"{kind}: graph-replayed sharded run == eager sharded run: {'OK' if good else 'MISMATCH'} (graph captured: {graphed._graph is not None})", flush=True)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_PARITY", "PASS" if ok else "FAIL", "world", world, flush=True)
