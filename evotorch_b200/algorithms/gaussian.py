@@ -157,8 +157,11 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         self._graph_counter = torch.zeros(1, dtype=torch.int32, device=dist.mu.device)
         self._graph_base_stream = prob._philox_stream
         graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count()
         with torch.cuda.graph(graph):
             self._graph_body(self._graph_base_stream, self._graph_counter)
+        self._graph_kernels = ops.launch_count() - before  # kernels of libevok.so inside one replay
+        ops.count_replayed_launches(-self._graph_kernels)  # the capture itself executed nothing
         self._graph_counter.zero_()
         self._graph = graph
 
@@ -171,6 +174,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             return
         prob._before_eval_hook(pop)
         self._graph.replay()
+        ops.count_replayed_launches(self._graph_kernels)
         prob._philox_stream += 1  # keep the host-side stream counter in step with the device-side one
         prob._finish_evaluation(pop)
 
@@ -207,7 +211,8 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
     def _step_distributed(self):
         """Every rank: sample/evaluate its shard, global ranking, all-reduced gradients, replicated update
         (replaces gaussian.py:199-272).  With `enable_cuda_graph()` the whole sequence, NCCL collectives included, is captured
-        once and replayed."""
+        once and replayed.  NOTE: replayed collectives run on the replaying stream, eager ones on NCCL's internal stream; do not
+        interleave a graph-mode searcher with other collectives on the same process group without a device synchronisation."""
         prob = self.problem
         if not (self._use_graph and self._graph_capturable()):
             self._graph = None
@@ -223,13 +228,17 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             base = prob._philox_stream
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
             with torch.cuda.graph(graph):
                 self._distributed_body(in_place=True)
                 prob.philox_stream_offset.add_(1)
+            self._graph_kernels = ops.launch_count() - before
+            ops.count_replayed_launches(-self._graph_kernels)
             prob._philox_stream = base  # the capture consumed one host-side stream id without running anything
             prob.philox_stream_offset.zero_()
             self._graph = graph
         self._graph.replay()
+        ops.count_replayed_launches(self._graph_kernels)
         prob._philox_stream += 1
 
     # ------------------------------------------------------------------ distribution update (K5)

@@ -66,9 +66,18 @@ def timer_results() -> dict:
     return out
 
 
+_replayed_launches = 0
+
+
+def count_replayed_launches(n: int) -> None:
+    """CUDA-graph replays re-run captured kernels without passing through the library: the searchers report them here."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    """Kernels launched by libevok.so so far in this process (exact: counted inside the library)."""
-    return int(nat.lib().evok_launch_count())
+    """Kernels of libevok.so launched so far in this process: direct launches (counted inside the library) + graph replays."""
+    return int(nat.lib().evok_launch_count()) + _replayed_launches
 
 
 def uses_kernels(t: torch.Tensor) -> bool:

@@ -50,18 +50,25 @@ for kind in ("pgpe", "snes", "cem"):
     ref = sharded.status["center"].clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, sharded.status["center"]), "ranks diverged"
-# CUDA-graph replay of the sharded generation (collectives captured) must equal the eager sharded run bit for bit
+# CUDA-graph replay of the sharded generation (collectives captured) must equal the eager sharded run bit for bit.
+# The two searchers run one after the other (never interleaved: replayed collectives use the replaying stream).
 for kind in ("pgpe", "snes"):
-    eager, graphed = make(kind, True), make(kind, True).enable_cuda_graph()
-    same = True
-    for gen in range(8):
-        eager.step()
-        graphed.step()
-        same = same and torch.equal(eager.status["center"], graphed.status["center"]) and torch.equal(eager.status["stdev"], graphed.status["stdev"])
-    good = same and graphed._graph is not None and abs(eager.status["mean_eval"] - graphed.status["mean_eval"]) < 1e-3
+    traj = {}
+    for mode in ("eager", "graph"):
+        s_ = make(kind, True)
+        if mode == "graph":
+            s_.enable_cuda_graph()
+        steps = []
+        for gen in range(8):
+            s_.step()
+            steps.append(torch.cat([s_.status["center"], s_.status["stdev"]]).clone())
+        traj[mode] = (torch.stack(steps), s_._graph is not None, s_.status["mean_eval"])
+        torch.cuda.synchronize()
+        dist.barrier()
+    good = torch.equal(traj["eager"][0], traj["graph"][0]) and traj["graph"][1] and not traj["eager"][1]
     ok = ok and good
     if rank == 0:
-        print(f"{kind}: graph-replayed sharded run == eager sharded run: {'OK' if good else 'MISMATCH'} (graph captured: {graphed._graph is not None})", flush=True)
+        print(f"{kind}: graph-replayed sharded run == eager sharded run: {'OK' if good else 'MISMATCH'} (graph captured: {traj['graph'][1]})", flush=True)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_PARITY", "PASS" if ok else "FAIL", "world", world, flush=True)
