@@ -296,11 +296,19 @@ def run_ours(args):
                "ms_per_step": e2e_ms / K,
                "api": "Problem.sample_and_compute_gradients(host-resident SymmetricSeparableGaussian) + update_parameters/modify_tensor on the host"}
 
+    def finish():
+        # leave without tearing the NCCL communicators down (teardown after graph-captured collectives can hang); every rank
+        # has passed the final barrier and rank 0 has flushed its JSON line
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(0)
+
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
 
     line = {
@@ -317,8 +325,7 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(args, steps=3, warmup=1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def run_reference(args):
