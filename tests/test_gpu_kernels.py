@@ -661,3 +661,43 @@ def test_config2_size_properties():
     m0 = s.status["mean_eval"]
     s.run(5)
     assert s.status["mean_eval"] < m0
+
+
+def test_metric_size_properties():
+    """BASELINE metric size: PGPE, popsize 1 000 000 x dim 10 000 (40 GB population on one B200) -- size-independent properties."""
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs 60 GB of free device memory")
+    n, D = 1_000_000, 10_000
+    prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=DEV, seed=7)
+    s = PGPE(prob, popsize=n, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+    s.step()
+    X, f = s.population.values, s.population.evals[:, 0]
+    mu, sg = s.status["center"], s.status["stdev"]
+    assert X.shape == (n, D) and bool(torch.isfinite(f).all())
+    rows = torch.randint(0, n // 2, (256,), device=DEV)
+    assert float((X[2 * rows] + X[2 * rows + 1] - 2 * mu).abs().max()) < 4e-6  # antithetic pairs
+    sub = torch.randint(0, n, (64,), device=DEV)
+    close(N(f[sub]), O.rastrigin(N(X[sub])), rtol=3e-6)  # fused fitness vs the float64 oracle on stored rows
+    # the last rows / columns were written (no tail bug at the full size) and follow the Philox restatement
+    tail = O.philox_population(N(mu), N(sg), 4, True, prob._philox_seed, 0, row0=n - 4)
+    close(N(X[n - 4:]), tail, rtol=0, atol=5e-5)
+    # ranking at N = 1 M with massive fp32 ties: bit-exact permutation of the utility table, stable order
+    perm = torch.empty(n, dtype=torch.int64, device=DEV)
+    w = ops.rank(f, "centered", False, perm=perm)
+    np.testing.assert_array_equal(N(torch.sort(w).values), np.arange(n, dtype=np.float32) / np.float32(n - 1) - np.float32(0.5))
+    np.testing.assert_array_equal(N(perm), O.argsort_for_ranking(N(f), False))
+    assert len(torch.unique(f)) < n  # there ARE ties at this size (SURVEY section 7.2)
+    # gradients: whole population == sum of 8 GPU-like shards; a full generation then moves the distribution
+    d = s._distribution
+    whole = d._compute_gradients(X, w, "centered")
+    acc = {k: torch.zeros(D, device=DEV) for k in ("mu", "sigma")}
+    for r in range(8):
+        lo, hi = r * n // 8, (r + 1) * n // 8
+        p = d.partial_gradients(X[lo:hi], w, lo, "centered")
+        for k in acc:
+            acc[k] += p[k]
+    for k in acc:
+        close(N(acc[k]), N(whole[k]), rtol=1e-3, atol=1e-7)
+    s.step()
+    assert not torch.equal(s.status["center"], mu) and bool(torch.isfinite(s.status["stdev"]).all())

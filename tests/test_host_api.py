@@ -283,3 +283,34 @@ def test_policy_cpu_matches_reference(golden):
         pol.set_parameters(torch.zeros(5))
     with pytest.raises(ValueError):
         Policy(net)(torch.zeros(2, 11))
+
+
+def test_searcher_pickles_and_resumes_identically():
+    import pickle
+
+    prob = Problem("min", sphere, initial_bounds=(-1, 1), solution_length=5, seed=3, vectorized=True)
+    s = PGPE(prob, popsize=10, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0)
+    s.run(3)
+    clone = pickle.loads(pickle.dumps(s))  # the reference checkpoints by pickling (logging.py:369-376, tools/cloning.py:258)
+    s.run(2)
+    clone.run(2)
+    assert torch.equal(s.status["center"], clone.status["center"]) and torch.equal(s.status["stdev"], clone.status["stdev"])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-sample-popsize", "64", "--dim", "200", "--popsize", "1000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
