@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from .. import ops
-from ..core import Problem, SolutionBatch
+from ..core import LazySolutionBatch, PhiloxRecipe, Problem, SolutionBatch
 from ..distributed import world
 from ..distributions import Distribution, ExpGaussian, ExpSeparableGaussian, SeparableGaussian, SymmetricSeparableGaussian
 from ..optimizers import get_optimizer_class
@@ -103,7 +103,10 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
     # ------------------------------------------------------------------ generations
     def _fill_and_eval_pop(self):
         if self._population is None:
-            self._population = SolutionBatch(self.problem, popsize=self._popsize, device=self._distribution.device, empty=True)
+            if self.problem.lazy_population:
+                self._population = LazySolutionBatch(self.problem, self._popsize, device=self._distribution.device)
+            else:
+                self._population = SolutionBatch(self.problem, popsize=self._popsize, device=self._distribution.device, empty=True)
         self.problem.sample_and_evaluate(self._distribution, self._population)
 
     # ------------------------------------------------------------------ CUDA-graph replay of a whole generation
@@ -140,13 +143,23 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
 
     def _graph_body(self, base_stream: int, counter: torch.Tensor):
         dist, prob, pop = self._distribution, self.problem, self._population
-        samples = pop._data
+        lazy = isinstance(pop, LazySolutionBatch)
+        n = len(pop)
         fitnesses = pop._evdata.view(-1)
+        if lazy:
+            # the population consumed here was drawn one stream id earlier (by the eager step before the capture, or by the previous replay)
+            samples = PhiloxRecipe(seed=prob._philox_seed, stream_id=base_stream - 1, row0=0, n_rows=n, solution_length=prob.solution_length,
+                                   symmetric=dist.SYMMETRIC, stream_offset=counter, mu=dist.mu, sigma=dist.sigma)
+        else:
+            samples = pop._data
         gradients = dist.compute_gradients(samples, fitnesses, objective_sense=prob.senses[self._obj_index], ranking_method=self._ranking_method)
         self._update_in_place(gradients)
-        ops.sample_eval(prob.evok_objective_id, samples, dist.mu, dist.sigma, n_rows=samples.shape[0], symmetric=dist.SYMMETRIC,
+        ops.sample_eval(prob.evok_objective_id, None if lazy else samples, dist.mu, dist.sigma, n_rows=n, symmetric=dist.SYMMETRIC,
                         seed=prob._philox_seed, stream_id=base_stream, f=fitnesses, stream_offset=counter)
         counter.add_(1)
+        if lazy:
+            pop.recipe = PhiloxRecipe(seed=prob._philox_seed, stream_id=base_stream - 1, row0=0, n_rows=n, solution_length=prob.solution_length,
+                                      symmetric=dist.SYMMETRIC, stream_offset=counter, mu=dist.mu, sigma=dist.sigma)
 
     def _capture_graph(self):
         prob = self.problem
@@ -191,7 +204,8 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             self._step_eager()
 
     def _step_eager(self):
-        samples = self._population.access_values(keep_evals=True)
+        lazy = isinstance(self._population, LazySolutionBatch)
+        samples = self._population.recipe if lazy else self._population.access_values(keep_evals=True)
         fitnesses = self._population.access_evals()[:, self._obj_index]
         gradients = self._distribution.compute_gradients(samples, fitnesses, objective_sense=self.problem.senses[self._obj_index],
                                                          ranking_method=self._ranking_method)

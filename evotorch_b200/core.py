@@ -51,7 +51,7 @@ class Problem:
                  solution_length: Optional[int] = None, dtype=None, eval_dtype=None, device=None, eval_data_length: Optional[int] = None,
                  seed: Optional[int] = None, num_actors=None, actor_config=None, num_gpus_per_actor=None, num_subbatches=None,
                  subbatch_size=None, store_solution_stats: Optional[bool] = None, vectorized: Optional[bool] = None,
-                 rng: Optional[str] = None):
+                 rng: Optional[str] = None, lazy_population: bool = False):
         if num_actors not in (None, 0):
             raise NotImplementedError(
                 "Ray actors are not part of evotorch_b200: shard the population over GPUs with torch.distributed instead "
@@ -117,6 +117,10 @@ class Problem:
         if rng not in ("philox", "torch"):
             raise ValueError(f"rng must be 'philox' or 'torch', got {rng!r}")
         self.rng = rng
+        # "lazy population": never materialise the N x D matrix.  The fused kernel evaluates the samples straight from the
+        # Philox counters and the gradient kernel regenerates them, so a generation needs O(N + D) memory (BASELINE config 5,
+        # 1 M x 100 k = 400 GB of samples, then runs on a single GPU).  Only for built-in objectives + the Philox sampler.
+        self.lazy_population = bool(lazy_population)
 
     # ------------------------------------------------------------------ construction helpers
     def _process_bounds(self, pair) -> tuple:
@@ -427,8 +431,24 @@ class Problem:
         """Fill `batch` with samples of `distribution` and evaluate it.  With a built-in objective, the Philox sampler and
         a separable Gaussian this is ONE kernel (K1+K2 fused: the population is written once and evaluated from registers);
         otherwise `distribution.sample(out=...)` followed by `evaluate` (gaussian.py:292-295 of the reference)."""
-        values = batch.access_values()
         obj = self.evok_objective_id
+        if isinstance(batch, LazySolutionBatch):
+            if not (obj is not None and self.rng == "philox" and len(self._senses) == 1 and hasattr(distribution, "SYMMETRIC")
+                    and ops.uses_kernels(distribution.mu)):
+                raise ValueError("a lazy population needs a built-in objective, rng='philox', a separable Gaussian and CUDA float32")
+            n = len(batch)
+            if distribution.SYMMETRIC and n % 2 != 0:
+                raise ValueError(f"Symmetric sampling cannot be done if the number of solutions is odd: {n}")
+            self._before_eval_hook(batch)
+            seed, stream_id = self.next_philox_stream()
+            mu, sigma = distribution.mu.contiguous(), distribution.sigma.contiguous()
+            batch.recipe = PhiloxRecipe(seed=seed, stream_id=stream_id, row0=self.philox_row0, n_rows=n, solution_length=self._solution_length,
+                                        symmetric=distribution.SYMMETRIC, stream_offset=self.philox_stream_offset, mu=mu, sigma=sigma)
+            ops.sample_eval(obj, None, mu, sigma, n_rows=n, symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id,
+                            row0=self.philox_row0, f=batch._evdata.view(-1), stream_offset=self.philox_stream_offset)
+            self._finish_evaluation(batch)
+            return
+        values = batch.access_values()
         fused = (obj is not None and self.rng == "philox" and ops.uses_kernels(values) and len(self._senses) == 1
                  and hasattr(distribution, "SYMMETRIC") and ops.uses_kernels(distribution.mu))
         if not fused:
@@ -728,6 +748,102 @@ class SolutionBatch:
 
     def __repr__(self) -> str:
         return f"<SolutionBatch: {len(self)} x {self.solution_length}, {self.dtype}, {self.device}>"
+
+
+class PhiloxRecipe:
+    """How a population was (and can again be) generated: stands in for the N x D sample matrix in the gradient calls."""
+
+    def __init__(self, *, seed: int, stream_id: int, row0: int, n_rows: int, solution_length: int, symmetric: bool,
+                 stream_offset: Optional[torch.Tensor], mu: torch.Tensor, sigma: torch.Tensor):
+        self.seed, self.stream_id, self.row0, self.n_rows = seed, stream_id, row0, n_rows
+        self.solution_length, self.symmetric, self.stream_offset = solution_length, symmetric, stream_offset
+        self.mu, self.sigma = mu, sigma
+
+    @property
+    def shape(self) -> tuple:
+        return (self.n_rows, self.solution_length)
+
+    def materialize(self) -> torch.Tensor:
+        """Regenerate the decision values (allocates n_rows x solution_length floats)."""
+        out = torch.empty(self.n_rows, self.solution_length, dtype=torch.float32, device=self.mu.device)
+        ops.sample_eval(ops.OBJ_NONE, out, self.mu, self.sigma, n_rows=self.n_rows, symmetric=self.symmetric, seed=self.seed,
+                        stream_id=self.stream_id, row0=self.row0, stream_offset=self.stream_offset)
+        return out
+
+
+class LazySolutionBatch(SolutionBatch):
+    """A population that exists only as fitnesses + a PhiloxRecipe.  `values` / `access_values()` regenerate the decision
+    values on demand (every call allocates); everything evaluation-related behaves like a SolutionBatch."""
+
+    def __init__(self, problem: "Problem", popsize: int, *, device=None):
+        device = problem.device if device is None else torch.device(device)
+        self._senses = problem.senses
+        self._num_objs = len(problem.senses)
+        self._popsize, self._solution_length = int(popsize), problem.solution_length
+        self._values_dtype = problem.dtype
+        self._evdata = torch.full((int(popsize), self._num_objs + problem.eval_data_length), float("nan"), dtype=problem.eval_dtype,
+                                  device=device)
+        self.recipe: Optional[PhiloxRecipe] = None
+
+    @property
+    def _data(self) -> torch.Tensor:
+        if self.recipe is None:
+            raise ValueError("This lazy population has not been sampled yet.")
+        return self.recipe.materialize()
+
+    def __len__(self) -> int:
+        return self._popsize
+
+    @property
+    def device(self) -> torch.device:
+        return self._evdata.device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self._values_dtype
+
+    values_dtype = dtype
+
+    @property
+    def solution_length(self) -> int:
+        return self._solution_length
+
+    @property
+    def values_shape(self) -> torch.Size:
+        return torch.Size((self._popsize, self._solution_length))
+
+    def access_values(self, *, keep_evals: bool = False) -> torch.Tensor:
+        if not keep_evals:
+            raise ValueError("The decision values of a lazy population are read-only (they are a function of the Philox counters).")
+        return self._data
+
+    def set_values(self, values: Any, *, solutions=None):
+        raise ValueError("The decision values of a lazy population are read-only (they are a function of the Philox counters).")
+
+    def __getitem__(self, i):
+        if isinstance(i, (slice, list, torch.Tensor)):
+            raise NotImplementedError("slicing a lazy population is not supported; use `.values` to materialise it")
+        i = int(i) % self._popsize
+        out = SolutionBatch(like=None, problem=None, popsize=None, slice_of=(_Materialized(self, i), slice(0, 1)))
+        return Solution(out, 0)
+
+    def __repr__(self) -> str:
+        return f"<LazySolutionBatch: {self._popsize} x {self._solution_length}, {self.device}>"
+
+
+class _Materialized:
+    """One regenerated row of a lazy population, shaped like a SolutionBatch source for `slice_of`."""
+
+    def __init__(self, lazy: LazySolutionBatch, i: int):
+        r = lazy.recipe
+        first = (i // 2) * 2 if r.symmetric else i
+        rows = 2 if r.symmetric else 1
+        block = torch.empty(rows, r.solution_length, dtype=torch.float32, device=r.mu.device)
+        ops.sample_eval(ops.OBJ_NONE, block, r.mu, r.sigma, n_rows=rows, symmetric=r.symmetric, seed=r.seed, stream_id=r.stream_id,
+                        row0=r.row0 + first, stream_offset=r.stream_offset)
+        self._data = block[i - first: i - first + 1]
+        self._evdata = lazy._evdata[i: i + 1]
+        self._senses, self._num_objs = lazy._senses, lazy._num_objs
 
 
 class Solution:

@@ -75,7 +75,7 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
     """One sample -> evaluate -> (global) rank -> gradient pass over this rank's row shard; see the module docstring.
     Returns {"gradients", "num_solutions", "mean_eval"} like the reference's `_sample_and_compute_gradients`
     (core.py:3156-3301), with gradients on `distribution.device`."""
-    from .core import SolutionBatch
+    from .core import LazySolutionBatch, SolutionBatch
 
     rank_, ws = world()
     home_device = distribution.device
@@ -89,14 +89,17 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
     cache = problem.__dict__.setdefault("_grad_batches", {})
     batch = cache.get(n_local)
     if batch is None:
-        batch = cache[n_local] = SolutionBatch(problem, n_local, device=problem.device, empty=True)
+        if problem.lazy_population:
+            batch = cache[n_local] = LazySolutionBatch(problem, n_local, device=problem.device)
+        else:
+            batch = cache[n_local] = SolutionBatch(problem, n_local, device=problem.device, empty=True)
     problem.philox_row0 = row0
     try:
         problem.sample_and_evaluate(dev_dist, batch)
     finally:
         problem.philox_row0 = 0
 
-    samples = batch.access_values(keep_evals=True)
+    samples = batch.recipe if isinstance(batch, LazySolutionBatch) else batch.access_values(keep_evals=True)
     f_local = batch.access_evals(obj_index)
     f_all = all_gather_rows(f_local.to(dev_dist.dtype), counts)
     sense = problem.senses[obj_index]

@@ -22,6 +22,7 @@ from typing import Any, Iterable, Optional
 import torch
 
 from . import ops
+from .core import PhiloxRecipe
 from .tools.misc import extract_generator, make_gaussian, to_torch_dtype
 from .tools.ranking import rank
 
@@ -241,6 +242,9 @@ class SeparableGaussian(Distribution):
     def _weighted_sums(self, form: int, samples: torch.Tensor, w: torch.Tensor, scale_mu: float, scale_sigma: float) -> tuple:
         """(scale_mu * sum_r a_r eps_r, scale_sigma * sum_r b_r g(eps_r)) -- the K4 kernel, or its torch restatement."""
         mu, sigma = self.mu, self.sigma
+        if isinstance(samples, PhiloxRecipe):  # lazy population: regenerate eps = sigma * z from the Philox counters
+            return ops.grad_regen(form, w.contiguous(), mu.contiguous(), sigma.contiguous(), seed=samples.seed, stream_id=samples.stream_id,
+                                  row0=samples.row0, scale_mu=scale_mu, scale_sigma=scale_sigma, stream_offset=samples.stream_offset)
         if ops.uses_kernels(samples) and ops.uses_kernels(w):
             return ops.grad(form, samples, w.contiguous(), mu.contiguous(), sigma.contiguous(), scale_mu, scale_sigma)
         if form == ops.GRAD_SYMMETRIC:

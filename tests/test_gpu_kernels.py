@@ -701,3 +701,68 @@ def test_metric_size_properties():
         close(N(acc[k]), N(whole[k]), rtol=1e-3, atol=1e-7)
     s.step()
     assert not torch.equal(s.status["center"], mu) and bool(torch.isfinite(s.status["stdev"]).all())
+
+
+# ------------------------------------------------------------------------------------------------ lazy (never materialised) population
+@pytest.mark.parametrize("algo", ["pgpe", "pgpe_plain_nonsym", "snes", "cem"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_lazy_population_matches_materialised(algo, graph):
+    """`Problem(lazy_population=True)`: fitnesses come straight from the Philox counters (X = NULL) and the gradient kernel
+    regenerates the samples.  The trajectory must agree with the materialised population to fp32 reduction-order noise."""
+    from evotorch_b200.core import LazySolutionBatch
+
+    def make(lazy):
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=515, device=DEV, seed=33, lazy_population=lazy)
+        if algo == "pgpe":
+            s = PGPE(prob, popsize=2000, center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+        elif algo == "pgpe_plain_nonsym":
+            s = PGPE(prob, popsize=2000, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0, symmetric=False, optimizer=None,
+                     ranking_method="nes", stdev_min=0.01, stdev_max=3.0)
+        elif algo == "snes":
+            s = SNES(prob, popsize=2000, stdev_init=2.0)
+        else:
+            s = CEM(prob, popsize=2000, parenthood_ratio=0.25, stdev_init=2.0, stdev_max_change=0.5)
+        return s.enable_cuda_graph() if (graph and lazy) else s
+
+    full, lazy = make(False), make(True)
+    for gen in range(6):
+        full.step()
+        lazy.step()
+        assert isinstance(lazy.population, LazySolutionBatch)
+        # same population, bit for bit (both are pure functions of (seed, generation, row, column, mu, sigma)) while mu/sigma agree
+        if gen == 0:
+            assert torch.equal(full.population.values, lazy.population.values)
+            assert torch.equal(full.population.evals, lazy.population.evals)
+        # (a different summation order inside the gradient kernel; a flipped near-tie in the ranking amplifies it a little per generation)
+        torch.testing.assert_close(lazy.status["center"], full.status["center"], rtol=0, atol=2e-4)
+        torch.testing.assert_close(lazy.status["stdev"], full.status["stdev"], rtol=0, atol=2e-4)
+    if graph:
+        assert lazy._graph is not None
+    # the regenerated values are consistent with the fitnesses the fused kernel produced
+    vals = lazy.population.values
+    torch.testing.assert_close(ops.evaluate(ops.OBJ_RASTRIGIN, vals), lazy.population.evals.view(-1), rtol=2e-6, atol=1e-3)
+    sol = lazy.population[7]
+    assert torch.equal(sol.values, vals[7]) and torch.equal(sol.evals, lazy.population.evals[7])
+    with pytest.raises(ValueError):
+        lazy.population.access_values()
+
+
+def test_lazy_population_needs_builtin_objective():
+    prob = Problem("min", lambda x: x.sum(-1), initial_bounds=(-1, 1), solution_length=16, device=DEV, vectorized=True, lazy_population=True)
+    with pytest.raises(ValueError, match="lazy population"):
+        SNES(prob, popsize=64, stdev_init=1.0).step()
+
+
+def test_lazy_population_runs_where_the_matrix_cannot_exist():
+    """popsize 8192 x dim 1M = 33 GB of samples per generation, never written.  Checks the footprint stays O(N + D) and the
+    search makes progress."""
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    prob = Problem("min", sphere, initial_bounds=(-1.0, 1.0), solution_length=1_000_000, device=DEV, seed=5, lazy_population=True)
+    s = PGPE(prob, popsize=8192, center_learning_rate=0.2, stdev_learning_rate=0.1, stdev_init=0.1)
+    s.step()
+    first = s.status["mean_eval"]
+    for _ in range(3):
+        s.step()
+    assert s.status["mean_eval"] < first
+    assert torch.cuda.max_memory_allocated() < 2 * 1024 ** 3
