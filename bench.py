@@ -49,10 +49,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=-1, help="1/0: replay each generation from a CUDA graph. Default: 0 at N = 1 (kernels are timed live inside the timed region), 1 at N > 1 (the captured graph includes the NCCL collectives: +5 %% at 2-8 GPUs; the fused kernel is then timed stand-alone right after the timed region)")
+    ap.add_argument("--peer", type=int, default=-1, help="1/0: at N > 1 move fitnesses and gradients between the GPUs from inside the producing kernels (NVLink peer memory, evotorch_b200/peer.py) instead of NCCL all_gather/all_reduce. Default: 1 at N > 1")
     return ap.parse_args()
 
 
-def workload_config(args, n_gpus):
+def workload_config(args, n_gpus, collectives="nccl"):
+    how = {"nccl": "NCCL all_gather(fitness) + all_reduce(grad)",
+           "peer": "fitness gather + gradient reduction fused into the producing kernels over NVLink peer memory (no NCCL in the loop)"}[collectives]
     return {
         "workload": f"PGPE(symmetric, ClipUp, centered ranking, stdev_max_change=0.2) on Rastrigin, popsize={args.popsize}, dim={args.dim}, fp32",
         "popsize": args.popsize,
@@ -60,7 +63,7 @@ def workload_config(args, n_gpus):
         "center_learning_rate": LR_MU,
         "stdev_learning_rate": LR_SIGMA,
         "stdev_init": STDEV_INIT,
-        "parallelism": f"population row-sharded over {n_gpus} GPU(s); allgather(fitness) + allreduce(grad)" if n_gpus > 1 else "single GPU",
+        "parallelism": f"population row-sharded over {n_gpus} GPU(s); {how}" if n_gpus > 1 else "single GPU",
         "l2": "inputs larger than L2 (population %.1f GB >> 126 MB): no flush needed" % (4.0 * args.popsize * args.dim / 1e9 / n_gpus),
     }
 
@@ -188,6 +191,15 @@ def run_ours(args):
         return float(t.item())
 
     problem = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=dev, seed=SEED)
+    collectives, px = "nccl", None
+    if world > 1 and (args.peer == 1 or args.peer < 0):
+        try:
+            from evotorch_b200.peer import enable_peer_exchange
+
+            px = enable_peer_exchange(problem, N)
+            collectives = "peer"
+        except Exception as exc:  # e.g. CUDA IPC not permitted in this container: keep the NCCL collectives (still the GPU path)
+            print(f"[bench] peer exchange unavailable ({exc!r}); using NCCL collectives", file=sys.stderr)
     searcher = PGPE(problem, popsize=N, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT,
                     distributed=(world > 1))
     use_graph = (world > 1) if args.cuda_graph < 0 else args.cuda_graph == 1
@@ -316,7 +328,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": elapsed_ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, world), cuda_graph=bool(use_graph)), "impl": "ours",
+        "config": dict(workload_config(args, world, collectives), cuda_graph=bool(use_graph)), "impl": "ours",
         "gpu_launches": int(launches), "clocks": clock_info, "e2e": e2e, "roofline": roofline, "kernels": kern,
         "whole_generation": {"model_bytes_per_gen_per_gpu": model_bytes, "model_gbs": model_bytes * value / 1e9,
                              "model_frac_of_peak": model_bytes * value / 1e9 / peak,
@@ -324,9 +336,13 @@ def run_ours(args):
                              "note": "model = SURVEY 8(d) 10*N*D bytes (unfused write+read+half read); moved = 6*N*D (evaluation fused into the sampling write)"},
         "mean_eval_after": mean_eval,
     }
+    if px is not None:
+        if px.timed_out():
+            raise RuntimeError("a peer-exchange wait timed out during the run: the numbers above are invalid")
+        line["peer_exchange"] = {"wait_timeouts": 0, "buffer_bytes": px.nbytes}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(args, steps=3, warmup=1)
-    print(json.dumps(line), flush=True)
+    emit(line)
     finish()
 
 
@@ -345,11 +361,33 @@ def run_reference(args):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to stdout when
+    the image sets NCCL_DEBUG): keep a private duplicate of the real stdout for the result and point fd 1 at stderr."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == "__main__":
     a = parse_args()
+    claim_stdout()
     try:
         if a.impl == "reference":
             run_reference(a)

@@ -444,8 +444,13 @@ class Problem:
             mu, sigma = distribution.mu.contiguous(), distribution.sigma.contiguous()
             batch.recipe = PhiloxRecipe(seed=seed, stream_id=stream_id, row0=self.philox_row0, n_rows=n, solution_length=self._solution_length,
                                         symmetric=distribution.SYMMETRIC, stream_offset=self.philox_stream_offset, mu=mu, sigma=sigma)
-            ops.sample_eval(obj, None, mu, sigma, n_rows=n, symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id,
-                            row0=self.philox_row0, f=batch._evdata.view(-1), stream_offset=self.philox_stream_offset)
+            peer = getattr(self, "_active_peer", None)
+            if peer is not None:  # sharded generation over NVLink peer memory: the fitness all-gather happens inside the kernel
+                ops.sample_eval_push(obj, None, mu, sigma, n_rows=n, symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id,
+                                     row0=self.philox_row0, peer=peer, stream_offset=self.philox_stream_offset)
+            else:
+                ops.sample_eval(obj, None, mu, sigma, n_rows=n, symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id,
+                                row0=self.philox_row0, f=batch._evdata.view(-1), stream_offset=self.philox_stream_offset)
             self._finish_evaluation(batch)
             return
         values = batch.access_values()
@@ -463,6 +468,13 @@ class Problem:
         evdata = batch._evdata
         direct = evdata.shape[1] == 1 and evdata.dtype == torch.float32 and evdata.is_contiguous()
         f = evdata.view(-1) if direct else torch.empty(n, dtype=torch.float32, device=values.device)
+        peer = getattr(self, "_active_peer", None)
+        if peer is not None:  # sharded generation over NVLink peer memory (evdata IS this rank's slice of peer.f_all)
+            ops.sample_eval_push(obj, values, distribution.mu.contiguous(), distribution.sigma.contiguous(), n_rows=n,
+                                 symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id, row0=self.philox_row0, peer=peer,
+                                 stream_offset=self.philox_stream_offset)
+            self._finish_evaluation(batch)
+            return
         ops.sample_eval(obj, values, distribution.mu.contiguous(), distribution.sigma.contiguous(), n_rows=n,
                         symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id, row0=self.philox_row0, f=f,
                         stream_offset=self.philox_stream_offset)

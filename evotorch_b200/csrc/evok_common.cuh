@@ -24,6 +24,42 @@ constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200
 
 // ------------------------------------------------------------------------------------------------
+// Peer exchange over NVLink (evok_peer.cu): where a producing kernel's result is needed by every GPU, the kernel itself
+// stores it into every peer's buffer and the LAST CTA to finish raises this rank's flag in every peer's flag array.
+// ------------------------------------------------------------------------------------------------
+struct PeerSink {
+  void* data[EVOK_MAX_PEERS];                 // peer p's destination buffer (this rank's own buffer at p == rank)
+  unsigned long long* flags[EVOK_MAX_PEERS];  // peer p's flag array (one 64-bit epoch per source rank)
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Call from ALL threads of EVERY CTA of a 1-D grid after the CTA's last peer store.  `epoch` (local) holds the number of
+// completed exchanges; the flag value raised is epoch + 1 (the waiting kernel advances `epoch`).  `done` is a local counter
+// that returns to 0 for the next launch.
+static __device__ __noinline__ void peer_signal_tail(const PeerSink& s, const unsigned long long* epoch, unsigned int* done) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's peer stores are visible system-wide before the counter moves
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      const unsigned long long e = *epoch + 1ull;
+      for (int p = 0; p < s.world; ++p) st_release_sys(s.flags[p] + s.rank, e);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  One call -> 4 x 32 random bits.
 // ------------------------------------------------------------------------------------------------
 struct U4 {

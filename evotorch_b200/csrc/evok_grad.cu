@@ -185,6 +185,45 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restr
   out_sigma[j] = t2 * scale_sigma;
 }
 
+// The same finalisation for the sharded generation: this rank's (grad_mu | grad_sigma) goes into slot `rank` of EVERY peer's
+// slot array (world x 2D floats) and the last CTA raises this rank's flag on every peer -- the send half of the all-reduce,
+// fused into the kernel that produces the data (the receive half is peer_reduce_kernel, evok_peer.cu).
+struct GradPush {
+  PeerSink sink;
+  const unsigned long long* epoch;
+  unsigned int* done;
+};
+
+__global__ void __launch_bounds__(256) grad_finalize_push_kernel(const float* __restrict__ partial, int n_chunks, int64_t D, float scale_mu,
+                                                                 float scale_sigma, const __grid_constant__ PeerSink sink,
+                                                                 const unsigned long long* epoch, unsigned int* done) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < D) {
+    float t1 = 0.0f, t2 = 0.0f;
+    for (int c = 0; c < n_chunks; ++c) {
+      t1 += partial[((int64_t)c * 2 + 0) * D + j];
+      t2 += partial[((int64_t)c * 2 + 1) * D + j];
+    }
+    t1 *= scale_mu;
+    t2 *= scale_sigma;
+    for (int p = 0; p < sink.world; ++p) {
+      float* slot = static_cast<float*>(sink.data[p]) + (int64_t)sink.rank * 2 * D;
+      slot[j] = t1;
+      slot[D + j] = t2;
+    }
+  }
+  peer_signal_tail(sink, epoch, done);
+}
+
+static int launch_finalize(const float* partial, int n_chunks, int64_t D, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma,
+                           const GradPush* push, cudaStream_t st) {
+  const unsigned grid = (unsigned)((D + 255) / 256);
+  if (push) grad_finalize_push_kernel<<<grid, 256, 0, st>>>(partial, n_chunks, D, scale_mu, scale_sigma, push->sink, push->epoch, push->done);
+  else grad_finalize_kernel<<<grid, 256, 0, st>>>(partial, n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // TMA-staged variant of the partial kernel: a producer warp streams row segments global -> shared with 1-D bulk async
 // copies (cp.async.bulk, completion counted on an mbarrier), S stages of R rows x 4 KB deep, so each SM keeps
@@ -396,8 +435,8 @@ static void launch_partial(const GradPlan& p, int form, const float* X, int64_t 
 
 static int grad_impl(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
                      int64_t D, bool regen, uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float scale_mu, float scale_sigma, float* out_mu,
-                     float* out_sigma, void* ws, size_t ws_bytes, void* stream) {
-  if (!w || !mu || !sigma || !out_mu || !out_sigma || !ws || (!regen && !X)) return EVOK_E_NULLPTR;
+                     float* out_sigma, void* ws, size_t ws_bytes, void* stream, const GradPush* push = nullptr) {
+  if (!w || !mu || !sigma || !ws || (!regen && !X) || (!push && (!out_mu || !out_sigma))) return EVOK_E_NULLPTR;
   if (form < EVOK_GRAD_SEPARABLE || form > EVOK_GRAD_MOMENTS) return EVOK_E_BADENUM;
   if (n_rows < 0 || D <= 0 || row0 < 0 || (!regen && ldx < D)) return EVOK_E_BADSIZE;
   const bool sym = form == EVOK_GRAD_SYMMETRIC;
@@ -410,6 +449,7 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
   const uint64_t unit0 = (uint64_t)(sym ? row0 / 2 : row0);
   GradPlan p = plan_grad(n_units, D, vec_ok);
   float* partial = (float*)ws;
+  if (n_units == 0 && push) return launch_finalize(partial, 0, D, scale_mu, scale_sigma, nullptr, nullptr, push, st);  // zeros + this rank's flag
   if (n_units == 0) {
     cudaMemsetAsync(out_mu, 0, (size_t)D * 4, st);
     cudaMemsetAsync(out_sigma, 0, (size_t)D * 4, st);
@@ -435,9 +475,7 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
       grad_partial_tma_kernel<false><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(form, X, ldx, w, mu, sigma, n_units, D, upc, partial);
     }
     EVOK_CHECK_LAUNCH();
-    grad_finalize_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(partial, n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
-    EVOK_CHECK_LAUNCH();
-    return 0;
+    return launch_finalize(partial, n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma, push, st);
   }
   if (regen) {
     if (sym) launch_partial<4, true, true>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
@@ -450,9 +488,7 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
     else launch_partial<1, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, unit0, seed, stream_id, stream_off, partial, st);
   }
   EVOK_CHECK_LAUNCH();
-  grad_finalize_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(partial, p.n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma);
-  EVOK_CHECK_LAUNCH();
-  return 0;
+  return launch_finalize(partial, p.n_chunks, D, scale_mu, scale_sigma, out_mu, out_sigma, push, st);
 }
 
 }  // namespace evok
@@ -477,4 +513,24 @@ extern "C" EVOK_API int evok_grad_regen(int form, const float* w, const float* m
                                float* out_mu, float* out_sigma, void* ws, size_t ws_bytes, void* stream) {
   return grad_impl(form, nullptr, 0, w, mu, sigma, row0, n_rows, D, true, seed, stream_id, stream_offset_dev, scale_mu, scale_sigma, out_mu, out_sigma, ws,
                    ws_bytes, stream);
+}
+
+extern "C" EVOK_API int evok_grad_push(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0,
+                                       int64_t n_rows, int64_t D, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev,
+                                       float scale_mu, float scale_sigma, int world, int rank, void* const* peer_slots, void* const* peer_flags,
+                                       const uint64_t* epoch_dev, uint32_t* done_dev, void* ws, size_t ws_bytes, void* stream) {
+  if (!peer_slots || !peer_flags || !epoch_dev || !done_dev) return EVOK_E_NULLPTR;
+  if (world < 1 || world > EVOK_MAX_PEERS || rank < 0 || rank >= world) return EVOK_E_BADSIZE;
+  GradPush push{};
+  push.sink.world = world;
+  push.sink.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_slots[p] || !peer_flags[p]) return EVOK_E_NULLPTR;
+    push.sink.data[p] = peer_slots[p];
+    push.sink.flags[p] = static_cast<unsigned long long*>(peer_flags[p]);
+  }
+  push.epoch = reinterpret_cast<const unsigned long long*>(epoch_dev);
+  push.done = done_dev;
+  return grad_impl(form, X, X ? ldx : 0, w, mu, sigma, row0, n_rows, D, X == nullptr, seed, stream_id, stream_offset_dev, scale_mu, scale_sigma, nullptr,
+                   nullptr, ws, ws_bytes, stream, &push);
 }

@@ -71,6 +71,22 @@ def broadcast_seed(problem) -> None:
     problem._seed_synced = True
 
 
+def _usable_peer_exchange(problem, dev_dist, popsize: int, ws: int):
+    """The PeerExchange attached to `problem` (peer.enable_peer_exchange) if this generation can run on it."""
+    peer = getattr(problem, "_peer_exchange", None)
+    if peer is None or ws == 1:
+        return None
+    from . import ops
+
+    ok = (peer.popsize == popsize and peer.world == ws and problem.evok_objective_id is not None and problem.rng == "philox"
+          and len(problem.senses) == 1 and problem.eval_data_length == 0 and hasattr(dev_dist, "partial_gradients")
+          and hasattr(dev_dist, "SYMMETRIC") and ops.uses_kernels(dev_dist.mu))
+    if not ok:
+        raise ValueError("the attached PeerExchange does not fit this generation (needs: same popsize and world size, a built-in "
+                         "objective, rng='philox', one objective, a separable Gaussian on CUDA float32)")
+    return peer
+
+
 def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_index: int, ranking_method: Optional[str]) -> dict:
     """One sample -> evaluate -> (global) rank -> gradient pass over this rank's row shard; see the module docstring.
     Returns {"gradients", "num_solutions", "mean_eval"} like the reference's `_sample_and_compute_gradients`
@@ -86,6 +102,7 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
     row0, n_local, counts = shard_rows(popsize, ws, rank_, symmetric)
     broadcast_seed(problem)
 
+    peer = _usable_peer_exchange(problem, dev_dist, popsize, ws)
     cache = problem.__dict__.setdefault("_grad_batches", {})
     batch = cache.get(n_local)
     if batch is None:
@@ -93,20 +110,34 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
             batch = cache[n_local] = LazySolutionBatch(problem, n_local, device=problem.device)
         else:
             batch = cache[n_local] = SolutionBatch(problem, n_local, device=problem.device, empty=True)
+        if peer is not None:  # the shard's fitness column IS its slice of the exchange buffer
+            batch._evdata = peer.f_all[row0:row0 + n_local].view(n_local, 1)
     problem.philox_row0 = row0
+    problem._active_peer = peer
     try:
         problem.sample_and_evaluate(dev_dist, batch)
     finally:
         problem.philox_row0 = 0
+        problem._active_peer = None
 
     samples = batch.recipe if isinstance(batch, LazySolutionBatch) else batch.access_values(keep_evals=True)
-    f_local = batch.access_evals(obj_index)
-    f_all = all_gather_rows(f_local.to(dev_dist.dtype), counts)
+    if peer is not None:
+        f_all = peer.wait_fitness()
+    else:
+        f_local = batch.access_evals(obj_index)
+        f_all = all_gather_rows(f_local.to(dev_dist.dtype), counts)
     sense = problem.senses[obj_index]
     method = "raw" if ranking_method is None else ranking_method
     weights_all = rank(f_all, method, higher_is_better=(sense == "max"))
 
-    if hasattr(dev_dist, "partial_gradients"):
+    if peer is not None:
+        dev_dist._peer = peer
+        try:
+            summed = dev_dist.partial_gradients(samples, weights_all, row0, method)  # already summed over the ranks
+        finally:
+            dev_dist._peer = None
+        grads = dev_dist.finalize_gradients(summed, popsize)
+    elif hasattr(dev_dist, "partial_gradients"):
         partial = dev_dist.partial_gradients(samples, weights_all, row0, method)
         if ws > 1:
             keys = sorted(partial)

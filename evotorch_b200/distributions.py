@@ -242,6 +242,14 @@ class SeparableGaussian(Distribution):
     def _weighted_sums(self, form: int, samples: torch.Tensor, w: torch.Tensor, scale_mu: float, scale_sigma: float) -> tuple:
         """(scale_mu * sum_r a_r eps_r, scale_sigma * sum_r b_r g(eps_r)) -- the K4 kernel, or its torch restatement."""
         mu, sigma = self.mu, self.sigma
+        peer = getattr(self, "_peer", None)
+        if peer is not None:  # sharded generation: the kernel pushes this shard's sums to every GPU, the reduction returns the global sums
+            if isinstance(samples, PhiloxRecipe):
+                ops.grad_push(form, None, w.contiguous(), mu.contiguous(), sigma.contiguous(), scale_mu=scale_mu, scale_sigma=scale_sigma, peer=peer,
+                              seed=samples.seed, stream_id=samples.stream_id, row0=samples.row0, stream_offset=samples.stream_offset)
+            else:
+                ops.grad_push(form, samples, w.contiguous(), mu.contiguous(), sigma.contiguous(), scale_mu=scale_mu, scale_sigma=scale_sigma, peer=peer)
+            return peer.reduce_gradients()
         if isinstance(samples, PhiloxRecipe):  # lazy population: regenerate eps = sigma * z from the Philox counters
             return ops.grad_regen(form, w.contiguous(), mu.contiguous(), sigma.contiguous(), seed=samples.seed, stream_id=samples.stream_id,
                                   row0=samples.row0, scale_mu=scale_mu, scale_sigma=scale_sigma, stream_offset=samples.stream_offset)

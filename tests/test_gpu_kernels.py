@@ -766,3 +766,74 @@ def test_lazy_population_runs_where_the_matrix_cannot_exist():
         s.step()
     assert s.status["mean_eval"] < first
     assert torch.cuda.max_memory_allocated() < 2 * 1024 ** 3
+
+
+# ------------------------------------------------------------------------------------------------ peer exchange (single-rank exercise of the kernels)
+@pytest.fixture
+def single_rank_group(tmp_path):
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists")
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    yield
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_kernels_single_rank(single_rank_group):
+    """World size 1 runs the very same kernels as the multi-GPU exchange (push stores + flag raise, flag wait, slot
+    reduction); the results must equal the plain kernels bit for bit, generation after generation, also from a CUDA graph.
+    (2- and 8-GPU parity: scripts/check_peer_exchange.py, profiles/r01_peer_exchange_*.txt.)"""
+    from evotorch_b200.peer import PeerExchange
+
+    n, d = 4096, 515
+    px = PeerExchange(n, d, torch.device(DEV), timeout_ns=2_000_000_000)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    mu = (torch.rand(d, generator=g) * 4 - 2).to(DEV)
+    sigma = (torch.rand(d, generator=g) + 0.5).to(DEV)
+    X, Xp = torch.empty(n, d, device=DEV), torch.empty(n, d, device=DEV)
+    f = torch.empty(n, device=DEV)
+
+    def generation(gen):
+        ops.sample_eval_push(ops.OBJ_RASTRIGIN, Xp, mu, sigma, n_rows=n, symmetric=True, seed=9, stream_id=gen, row0=0, peer=px)
+        f_all = px.wait_fitness()
+        w = ops.rank(f_all, "centered", False)
+        ops.grad_push(ops.GRAD_SYMMETRIC, Xp, w, mu, sigma, scale_mu=2.0 / n, scale_sigma=2.0 / n, peer=px)
+        return f_all, w, px.reduce_gradients()
+
+    for gen in range(3):
+        f_all, w, (gmu, gsig) = generation(gen)
+        ops.sample_eval(ops.OBJ_RASTRIGIN, X, mu, sigma, n_rows=n, symmetric=True, seed=9, stream_id=gen, f=f)
+        rmu, rsig = ops.grad(ops.GRAD_SYMMETRIC, X, w, mu, sigma, 2.0 / n, 2.0 / n)
+        assert torch.equal(X, Xp) and torch.equal(f, f_all), gen
+        assert torch.equal(gmu, rmu) and torch.equal(gsig, rsig), gen
+    assert px._epochs.tolist() == [3, 3] and not px.timed_out()
+
+    # the regenerating (lazy) producer and CUDA-graph replay
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        w = ops.rank(px.f_all, "centered", False)
+        ops.grad_push(ops.GRAD_SYMMETRIC, None, w, mu, sigma, scale_mu=2.0 / n, scale_sigma=2.0 / n, peer=px, seed=9, stream_id=2, row0=0)
+        px.reduce_gradients()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            ops.grad_push(ops.GRAD_SYMMETRIC, None, w, mu, sigma, scale_mu=2.0 / n, scale_sigma=2.0 / n, peer=px, seed=9, stream_id=2, row0=0)
+            out = px.reduce_gradients()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out[0], rmu, rtol=0, atol=2e-6)
+    torch.testing.assert_close(out[1], rsig, rtol=0, atol=2e-6)
+    assert px._epochs.tolist() == [3, 7] and not px.timed_out()
+    px.close()
+
+
+def test_peer_wait_times_out_instead_of_hanging(single_rank_group):
+    from evotorch_b200.peer import PeerExchange
+
+    px = PeerExchange(64, 8, torch.device(DEV), timeout_ns=20_000_000)  # 20 ms
+    px.wait_fitness()  # nobody raised the flag
+    assert px.timed_out()
+    px.close()
