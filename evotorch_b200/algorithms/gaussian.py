@@ -100,6 +100,13 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
                        device=self._distribution.device)
         return optimizer
 
+    # ------------------------------------------------------------------ pickling (checkpoints: logging.PicklingLogger(checkpoint=True))
+    def __getstate__(self) -> dict:
+        """Everything but the captured CUDA graph (re-captured on the first step after loading)."""
+        state = dict(self.__dict__)
+        state["_graph"] = None
+        return state
+
     # ------------------------------------------------------------------ generations
     def _fill_and_eval_pop(self):
         if self._population is None:

@@ -426,6 +426,17 @@ class Problem:
                         worst_eval=float(self._worst[0].evals[0]))
         return {"best": self._best, "worst": self._worst}
 
+    # ------------------------------------------------------------------ pickling (core.py:2711-2734)
+    _TRANSIENT = ("_peer_exchange", "_active_peer", "_grad_batches")
+
+    def __getstate__(self) -> dict:
+        """Device-mapped and cached objects (peer-exchange buffers, gradient batches, the CUDA-graph generation counter) are
+        not part of a pickled problem; the Philox key and the host-side generation counter are, so an unpickled problem
+        continues the same random stream."""
+        state = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT}
+        state["philox_stream_offset"] = None
+        return state
+
     # ------------------------------------------------------------------ fused sample + evaluate, gradient service
     def sample_and_evaluate(self, distribution, batch: "SolutionBatch"):
         """Fill `batch` with samples of `distribution` and evaluate it.  With a built-in objective, the Philox sampler and

@@ -2,7 +2,11 @@
 
 from __future__ import annotations
 
-from typing import Iterable, Optional
+import os
+import pickle
+import weakref
+from datetime import datetime
+from typing import Any, Iterable, Optional, Union
 
 import torch
 
@@ -82,3 +86,102 @@ class PandasLogger(ScalarLogger):
         if index is not None and index in df.columns:
             df.set_index(index, inplace=True)
         return df
+
+
+class PicklingLogger(Logger):
+    """Every `interval` generations (and at the end of a run) pickle the chosen status items -- as host tensors, so the file loads
+    on a machine without a GPU -- into `<directory>/<prefix>_generation<NNNNNN>.pickle` (logging.py:111-392).
+
+    `items_to_save` are status keys ("center", "best", ...); `Solution`s are stored as their decision values.  The file
+    also carries "beginning_time" / "now" / "elapsed".  With `checkpoint=True` the whole searcher (distribution, optimizer
+    state, Philox key and generation counter) is stored under the key "searcher": `resume(file)` returns a searcher that
+    continues the very same trajectory (the sampler is counter based, so the resumed run is bit-identical to an
+    uninterrupted one)."""
+
+    def __init__(self, searcher, *, interval: int, directory: Optional[str] = None, prefix: Optional[str] = None, zfill: int = 6,
+                 items_to_save: Union[str, Iterable[str]] = ("center", "best"), after_first_step: bool = False, verbose: bool = True,
+                 checkpoint: bool = False):
+        super().__init__(searcher, interval=interval, after_first_step=after_first_step)
+        self._searcher_ref = weakref.ref(searcher)
+        self._items_to_save = (items_to_save,) if isinstance(items_to_save, str) else tuple(items_to_save)
+        if prefix is None:
+            prefix = f"{type(searcher.problem).__name__}_{datetime.now().strftime('%Y-%m-%d-%H.%M.%S')}_{os.getpid()}"
+        self._prefix = str(prefix)
+        self._directory = None if directory is None else str(directory)
+        if self._directory is not None:
+            os.makedirs(self._directory, exist_ok=True)
+        self._verbose, self._zfill, self._checkpoint = bool(verbose), int(zfill), bool(checkpoint)
+        self._last_generation: Optional[int] = None
+        self._last_file_name: Optional[str] = None
+
+    def __getstate__(self) -> dict:
+        state = dict(self.__dict__)
+        state["_searcher_ref"] = None  # weak references do not pickle; `resume` re-binds
+        return state
+
+    @staticmethod
+    def _as_cpu(x: Any) -> Any:
+        from .core import Solution
+
+        if isinstance(x, Solution):
+            x = x.values
+        if isinstance(x, torch.Tensor):
+            x = x.detach().to("cpu").clone()
+        return x
+
+    def _log(self, status: dict):
+        self.save()
+
+    def _final(self, status: dict):
+        searcher = self._searcher_ref() if self._searcher_ref is not None else None
+        if searcher is not None and (self._last_generation is None or searcher.step_count > self._last_generation):
+            self.save()
+
+    def save(self, fname: Optional[str] = None) -> Optional[str]:
+        """Write the pickle now; returns the file name (None if the searcher is gone)."""
+        searcher = self._searcher_ref() if self._searcher_ref is not None else None
+        if searcher is None:
+            return None
+        status = searcher.status
+        data = {k: self._as_cpu(status[k]) for k in self._items_to_save if k in status}
+        begun = searcher.first_step_datetime
+        if begun is not None:
+            now = datetime.now()
+            data.update(beginning_time=begun, now=now, elapsed=now - begun)
+        if self._checkpoint:
+            data["searcher"] = searcher
+        if fname is None:
+            fname = f"{self._prefix}_generation{str(searcher.step_count).zfill(self._zfill)}.pickle"
+        if self._directory is not None:
+            fname = os.path.join(self._directory, str(fname))
+        with open(fname, "wb") as f:
+            pickle.dump(data, f)
+        self._last_generation, self._last_file_name = searcher.step_count, str(fname)
+        if self._verbose:
+            print("Saved to", fname)
+        return str(fname)
+
+    @property
+    def last_generation(self) -> Optional[int]:
+        return self._last_generation
+
+    @property
+    def last_file_name(self) -> Optional[str]:
+        return self._last_file_name
+
+    def unpickle_last_file(self) -> dict:
+        with open(self._last_file_name, "rb") as f:
+            return pickle.load(f)
+
+    @staticmethod
+    def resume(fname: str):
+        """The searcher stored by a `checkpoint=True` logger, ready to `step()` / `run()` on."""
+        with open(fname, "rb") as f:
+            data = pickle.load(f)
+        if "searcher" not in data:
+            raise KeyError(f"{fname} holds no searcher: create the PicklingLogger with checkpoint=True")
+        searcher = data["searcher"]
+        for hook in list(searcher.log_hook):
+            if isinstance(hook, PicklingLogger):
+                hook._searcher_ref = weakref.ref(searcher)
+        return searcher

@@ -837,3 +837,30 @@ def test_peer_wait_times_out_instead_of_hanging(single_rank_group):
     px.wait_fitness()  # nobody raised the flag
     assert px.timed_out()
     px.close()
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "lazy_graph"])
+def test_checkpoint_resume_is_bit_identical_on_gpu(tmp_path, mode):
+    """A searcher pickled mid-run (PicklingLogger(checkpoint=True)) continues exactly like the uninterrupted one: the
+    sampler is counter based, the captured CUDA graph is dropped from the pickle and re-captured after loading."""
+    from evotorch_b200.logging import PicklingLogger
+
+    def make():
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=200, device=DEV, seed=4, lazy_population=mode.startswith("lazy"))
+        s = PGPE(prob, popsize=500, center_learning_rate=0.4, stdev_learning_rate=0.1, stdev_init=1.0)
+        return s.enable_cuda_graph() if mode.endswith("graph") else s
+
+    straight = make()
+    straight.run(11)
+    s = make()
+    logger = PicklingLogger(s, interval=5, directory=str(tmp_path), prefix="gpu", verbose=False, checkpoint=True)
+    s.run(5)
+    data = logger.unpickle_last_file()
+    assert data["center"].device.type == "cpu" and torch.equal(data["center"], s.status["center"].cpu())
+    resumed = PicklingLogger.resume(logger.last_file_name)
+    assert resumed._graph is None and resumed.step_count == 5
+    resumed.run(6)
+    assert (resumed._graph is not None) == mode.endswith("graph")
+    assert torch.equal(resumed.status["center"], straight.status["center"])
+    assert torch.equal(resumed.status["stdev"], straight.status["stdev"])
+    assert resumed.status["mean_eval"] == straight.status["mean_eval"]

@@ -1,6 +1,7 @@
 """The host-side mirror of the reference API on CPU tensors (BASELINE config 1 path): seeded trajectories of the package
 must reproduce the REAL reference's trajectories recorded in tests/golden (same torch RNG stream => same populations)."""
 
+import os
 import math
 
 import numpy as np
@@ -314,3 +315,45 @@ def test_bench_reference_arm_prints_one_json_line():
                 "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+
+
+# ------------------------------------------------------------------------------------------------ pickling / checkpoints
+def test_pickling_logger_files_items_and_resume(tmp_path, capsys):
+    import pickle
+
+    from evotorch_b200.logging import PicklingLogger
+
+    def make():
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=12, vectorized=True, seed=11)
+        return PGPE(prob, popsize=40, center_learning_rate=0.3, stdev_learning_rate=0.1, stdev_init=1.0)
+
+    straight = make()
+    straight.run(9)
+
+    s = make()
+    logger = PicklingLogger(s, interval=3, directory=str(tmp_path / "ckpt"), prefix="run", items_to_save=("center", "stdev", "best", "nope"),
+                            checkpoint=True)
+    s.run(4)
+    files = sorted(os.listdir(tmp_path / "ckpt"))
+    assert files == ["run_generation000003.pickle", "run_generation000004.pickle"]  # every 3rd generation + the end of the run
+    assert logger.last_generation == 4 and logger.last_file_name.endswith("run_generation000004.pickle")
+    assert "Saved to" in capsys.readouterr().out
+    data = logger.unpickle_last_file()
+    assert set(data) >= {"center", "stdev", "best", "beginning_time", "now", "elapsed", "searcher"} and "nope" not in data
+    assert torch.equal(data["center"], s.status["center"]) and data["center"].device.type == "cpu"
+    assert data["best"].shape == (12,)  # a Solution is stored as its decision values
+    # resume from the generation-3 file: the continued run must be the uninterrupted run, bit for bit
+    resumed = PicklingLogger.resume(str(tmp_path / "ckpt" / "run_generation000003.pickle"))
+    assert resumed.step_count == 3
+    resumed.run(6)
+    assert torch.equal(resumed.status["center"], straight.status["center"])
+    assert torch.equal(resumed.status["stdev"], straight.status["stdev"])
+    # the resumed searcher keeps checkpointing through its (re-bound) logger
+    assert "run_generation000009.pickle" in os.listdir(tmp_path / "ckpt")
+    # plain pickles of problem and searcher round-trip too
+    clone = pickle.loads(pickle.dumps(s))
+    clone.step(); s.step()
+    assert torch.equal(clone.status["center"], s.status["center"])
+    with pytest.raises(KeyError):
+        lg = PicklingLogger(s, interval=1, directory=str(tmp_path / "plain"), prefix="p", verbose=False)
+        PicklingLogger.resume(lg.save())
