@@ -10,7 +10,7 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
  *   - the caller owns all memory, including workspaces (query the *_workspace_bytes functions);
- *     the library never allocates, frees or synchronises;
+ *     the library never allocates, frees or synchronises (the one exception: evok_peer_alloc / open / close / free);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, so every call is
  *     CUDA-graph capturable and re-entrant;
  *   - return value: 0 = ok, negative = argument error (EVOK_E_*), positive = cudaError_t;
