@@ -209,29 +209,29 @@ int evok_transpose_scale(const float* in, int64_t ldi, int64_t rows, int64_t col
  *   evok_peer_alloc / open / close / free : the only entry points that allocate.  `handle` is a 64-byte cudaIpcMemHandle_t
  *       to be passed to the other processes (any transport).  The buffer is zero-filled.
  *   evok_sample_eval_push : evok_sample_eval whose fitness store goes to row (row0 + i) of EVERY peer's fitness vector
- *       (peer_f[p] = base of peer p's N-float vector) -- the all-gather.  The last CTA raises flag[rank] = *epoch_dev + 1 in
- *       every peer's flag array (peer_flags[p] = base of peer p's `world` 64-bit flags).
+ *       (peer_f_host[p] = base of peer p's N-float vector; the *_host tables are host arrays of `world` device pointers) -- the all-gather.  The last CTA raises flag[rank] = *epoch_dev + 1 in
+ *       every peer's flag array (peer_flags_host[p] = base of peer p's `world` 64-bit flags).
  *   evok_peer_wait : one warp spins until all `world` local flags reach *epoch_dev + 1, then advances *epoch_dev.  After
  *       `timeout_ns` it gives up, sets *err_dev = 1 and advances anyway (no hang; the host checks err_dev when it likes).
  *   evok_grad_push : evok_grad / evok_grad_regen (X == NULL) whose finalisation writes this rank's (grad_mu | grad_sigma)
- *       into slot `rank` of every peer's slot array (peer_slots[p] = base of world x 2D floats) and raises the flags.
+ *       into slot `rank` of every peer's slot array (peer_slots_host[p] = base of world x 2D floats) and raises the flags.
  *   evok_peer_reduce : waits like evok_peer_wait, then out[j] = sum over ranks (in rank order: bit-identical on every GPU)
  *       of slots[r * n + j] -- the all-reduce.
  * `done_dev` is a zero-initialised local uint32 per exchange point; `epoch_dev` a zero-initialised local uint64 per
  * exchange point.  Everything is stream-ordered and CUDA-graph capturable (the pointers are baked into the launch).
  * --------------------------------------------------------------------------------------------- */
-int evok_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out_64B);
-int evok_peer_open(const void* handle_64B, void** dev_ptr);
+int evok_peer_alloc(size_t bytes, void** dev_ptr_out_host, void* handle_out_64B_host);
+int evok_peer_open(const void* handle_64B_host, void** dev_ptr_out_host);
 int evok_peer_close(void* dev_ptr);
 int evok_peer_free(void* dev_ptr);
 int evok_sample_eval_push(int objective, float* X, int64_t ldx, const float* mu, const float* sigma, int64_t row0, int64_t n_rows,
                           int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, int world,
-                          int rank, void* const* peer_f, void* const* peer_flags, const uint64_t* epoch_dev, uint32_t* done_dev,
+                          int rank, void* const* peer_f_host, void* const* peer_flags_host, const uint64_t* epoch_dev, uint32_t* done_dev,
                           void* stream);
 int evok_peer_wait(const uint64_t* flags_local, int world, uint64_t* epoch_dev, uint32_t* err_dev, uint64_t timeout_ns, void* stream);
 int evok_grad_push(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0,
                    int64_t n_rows, int64_t D, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, float scale_mu,
-                   float scale_sigma, int world, int rank, void* const* peer_slots, void* const* peer_flags,
+                   float scale_sigma, int world, int rank, void* const* peer_slots_host, void* const* peer_flags_host,
                    const uint64_t* epoch_dev, uint32_t* done_dev, void* ws, size_t ws_bytes, void* stream);
 int evok_peer_reduce(const float* slots_local, int world, int64_t n, const uint64_t* flags_local, uint64_t* epoch_dev,
                      uint32_t* done_dev, uint32_t* err_dev, uint64_t timeout_ns, float* out, void* stream);
