@@ -90,11 +90,35 @@ def cpu_reference_run(args, steps: int, warmup: int) -> dict:
     dt = time.perf_counter() - t0
     sample_gps = steps / dt
     full_gps = sample_gps * (n_sample / args.popsize)
+    torch_eager_gpu = None
+    if torch.cuda.is_available() and args.impl != "reference":
+        # the same torch op sequence, eager, on this GPU ("PyTorch path" comparator); bounded sample, scaled like the CPU leg
+        try:
+            n_gpu = min(100_000, args.popsize)
+            n_gpu -= n_gpu % 2
+            gpath = PGPEReferencePath(args.dim, n_gpu, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT, seed=SEED,
+                                      device="cuda")
+            for _ in range(3):
+                gpath.step()
+            torch.cuda.synchronize()
+            g0 = time.perf_counter()
+            for _ in range(10):
+                gpath.step()
+            torch.cuda.synchronize()
+            gdt = (time.perf_counter() - g0) / 10
+            torch_eager_gpu = {"value": (1.0 / gdt) * (n_gpu / args.popsize), "unit": UNIT,
+                               "sample": f"10 generations at popsize={n_gpu} x dim={args.dim} ({1e3 * gdt:.2f} ms each), scaled linearly in popsize "
+                                         f"to {args.popsize}; the reference's torch op sequence, eager, on cuda:0"}
+            del gpath
+            torch.cuda.empty_cache()
+        except Exception as exc:  # e.g. out of memory for the temporaries: report, do not fail the bench
+            torch_eager_gpu = {"unavailable": repr(exc)[:200]}
     return {
         "value": full_gps,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
+        "torch_eager_gpu": torch_eager_gpu,
         "sample": f"{steps} generations at popsize={n_sample} x dim={args.dim} ({dt:.2f} s, {sample_gps:.4f} gen/s); "
                   f"scaled linearly in popsize to {args.popsize}; torch {torch.__version__} CPU, {torch.get_num_threads()} threads",
         "sample_ms_per_step": 1e3 * dt / steps,

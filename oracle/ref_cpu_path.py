@@ -33,25 +33,28 @@ class PGPEReferencePath:
 
     def __init__(self, solution_length: int, popsize: int, *, center_learning_rate: float, stdev_learning_rate: float, stdev_init: float,
                  seed: int, stdev_max_change: Optional[float] = 0.2, momentum: float = 0.9, sense: str = "min",
-                 center_init: Optional[torch.Tensor] = None, objective=rastrigin):
+                 center_init: Optional[torch.Tensor] = None, objective=rastrigin, device: str = "cpu"):
+        # `device="cuda"` runs the very same torch op sequence on a GPU (the reference is device-agnostic): the "PyTorch eager
+        # on the same B200" comparator of SURVEY 8(d).  The CPU trajectory is what the golden tests pin.
         self.n, self.d = int(popsize), int(solution_length)
-        self.gen = torch.Generator().manual_seed(int(seed))
+        self.device = torch.device(device)
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
         if center_init is None:  # Problem.generate_values(1): uniform_() * (ub - lb) + lb  (core.py:1840-1909, tools/misc.py:1540)
-            mu = torch.empty(1, self.d)
+            mu = torch.empty(1, self.d, device=self.device)
             mu.uniform_(generator=self.gen)
             mu *= torch.tensor(5.12) - torch.tensor(-5.12)
             mu += torch.tensor(-5.12)
             self.mu = mu.reshape(-1)
         else:
-            self.mu = center_init.clone()
-        self.sigma = torch.full((self.d,), float(stdev_init))
+            self.mu = center_init.clone().to(self.device)
+        self.sigma = torch.full((self.d,), float(stdev_init), device=self.device)
         self.lr, self.lr_sigma = float(center_learning_rate), float(stdev_learning_rate)
         self.momentum, self.max_speed = float(momentum), 2.0 * float(center_learning_rate)
-        self.velocity = torch.zeros(self.d)
+        self.velocity = torch.zeros(self.d, device=self.device)
         self.max_change = stdev_max_change
         self.sense = sense
         self.objective = objective
-        self.X = torch.empty(self.n, self.d)
+        self.X = torch.empty(self.n, self.d, device=self.device)
         self.f: Optional[torch.Tensor] = None
         self.first = True
 
@@ -68,7 +71,7 @@ class PGPEReferencePath:
         x, f = self.X, self.f
         n = len(f)
         indices = f.argsort(descending=(self.sense != "max"))
-        weights = (torch.arange(n, dtype=f.dtype) / (n - 1)) - 0.5
+        weights = (torch.arange(n, dtype=f.dtype, device=f.device) / (n - 1)) - 0.5
         ranks = torch.empty_like(f)
         ranks[indices] = weights
         scaled_noises = x[0::2] - self.mu
