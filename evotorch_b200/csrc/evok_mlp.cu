@@ -25,6 +25,29 @@ struct MlpSpec {
   int max_width;
 };
 
+// Observation pre-processing of the rollout loop (vecgymne.py:604-660, 822-836; net/runningnorm.py:412-533), fused into the
+// observation load: x = clamp((obs - mean) / stdev, lo, hi) with mean / stdev derived on the fly from the running sums
+// (mean = sum / count, var = max(sumsq / count - mean^2, min_variance)); policies whose environment is inactive are skipped
+// altogether -- their 4*L parameter bytes are never read -- and get zero actions.
+struct ObsPrep {
+  const float* sum;        // n_in running sums, nullptr = no normalisation
+  const float* sumsq;      // n_in running sums of squares
+  const long long* count;  // number of observations behind the sums (device scalar)
+  const unsigned char* active;  // N flags, nullptr = all active
+  float min_variance, lo, hi;   // lo / hi = NaN: no clipping on that side
+};
+
+__device__ __forceinline__ float prep_obs(const ObsPrep& p, int k, float o) {
+  if (!p.sum) return o;
+  const float n = (float)(*p.count);
+  const float mean = __fdiv_rn(p.sum[k], n);
+  const float var = fmaxf(__fdiv_rn(p.sumsq[k], n) - mean * mean, p.min_variance);
+  float v = __fdiv_rn(o - mean, __fsqrt_rn(var));
+  if (p.lo == p.lo) v = fmaxf(v, p.lo);
+  if (p.hi == p.hi) v = fminf(v, p.hi);
+  return v;
+}
+
 __device__ __forceinline__ float activate(float v, int act) {
   switch (act) {
     case EVOK_ACT_TANH: return tanhf(v);
@@ -46,11 +69,15 @@ __device__ __forceinline__ void store_shifted(float* buf, int ph, int j, float v
 
 __global__ void __launch_bounds__(kMlpThreads)
     mlp_forward_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ obs, int64_t ldo, float* __restrict__ out,
-                       int64_t ldout, int64_t N, const __grid_constant__ MlpSpec spec) {
+                       int64_t ldout, int64_t N, const __grid_constant__ MlpSpec spec, const __grid_constant__ ObsPrep prep) {
   extern __shared__ __align__(16) float act_buf[];  // 2 x (max_width + 2 * kMlpPad)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stride = (spec.max_width + 2 * kMlpPad + 3) & ~3;  // keeps both ping-pong buffers 16-byte aligned
   for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+    if (prep.active && !prep.active[i]) {  // CTA-uniform: the whole policy is skipped
+      for (int k = threadIdx.x; k < spec.dims[spec.n_layers]; k += kMlpThreads) out[i * ldout + k] = 0.0f;
+      continue;
+    }
     const float* prow = params + i * ldp;
     const bool edge_row = (i == 0) || (i == N - 1);
     float* cur = act_buf;
@@ -59,7 +86,7 @@ __global__ void __launch_bounds__(kMlpThreads)
     int ph = (int)((reinterpret_cast<uintptr_t>(prow + spec.w_off[0]) >> 2) & 3);
     for (int k = threadIdx.x; k < stride; k += kMlpThreads) cur[k] = 0.0f;
     __syncthreads();
-    for (int k = threadIdx.x; k < spec.dims[0]; k += kMlpThreads) store_shifted(cur, ph, k, ld_stream1(obs + i * ldo + k));
+    for (int k = threadIdx.x; k < spec.dims[0]; k += kMlpThreads) store_shifted(cur, ph, k, prep_obs(prep, k, ld_stream1(obs + i * ldo + k)));
     __syncthreads();
     for (int l = 0; l < spec.n_layers; ++l) {
       const int n_in = spec.dims[l], n_out = spec.dims[l + 1];
@@ -126,8 +153,8 @@ extern "C" EVOK_API int64_t evok_mlp_parameter_length(int n_layers, const int32_
   return total;
 }
 
-extern "C" EVOK_API int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout,
-                                         int64_t N, int n_layers, const int32_t* dims_host, const int32_t* acts_host, void* stream) {
+static int mlp_forward_impl(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N, int n_layers,
+                            const int32_t* dims_host, const int32_t* acts_host, const ObsPrep& prep, void* stream) {
   if (!params || !obs || !out || !dims_host || !acts_host) return EVOK_E_NULLPTR;
   if (n_layers < 1 || n_layers > kMlpMaxLayers || N < 0) return EVOK_E_BADSIZE;
   MlpSpec spec;
@@ -157,7 +184,29 @@ extern "C" EVOK_API int evok_mlp_forward(const float* params, int64_t ldp, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > N) grid = N;
-  mlp_forward_kernel<<<(unsigned)grid, kMlpThreads, smem, (cudaStream_t)stream>>>(params, ldp, obs, ldo, out, ldout, N, spec);
+  mlp_forward_kernel<<<(unsigned)grid, kMlpThreads, smem, (cudaStream_t)stream>>>(params, ldp, obs, ldo, out, ldout, N, spec, prep);
   EVOK_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" EVOK_API int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout,
+                                         int64_t N, int n_layers, const int32_t* dims_host, const int32_t* acts_host, void* stream) {
+  ObsPrep prep{};
+  return mlp_forward_impl(params, ldp, obs, ldo, out, ldout, N, n_layers, dims_host, acts_host, prep, stream);
+}
+
+extern "C" EVOK_API int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
+                                              int n_layers, const int32_t* dims_host, const int32_t* acts_host, const float* obs_sum,
+                                              const float* obs_sumsq, const int64_t* obs_count_dev, float min_variance, float clip_lo, float clip_hi,
+                                              const uint8_t* active, void* stream) {
+  if ((obs_sum != nullptr) != (obs_sumsq != nullptr) || (obs_sum != nullptr) != (obs_count_dev != nullptr)) return EVOK_E_NULLPTR;
+  ObsPrep prep{};
+  prep.sum = obs_sum;
+  prep.sumsq = obs_sumsq;
+  prep.count = reinterpret_cast<const long long*>(obs_count_dev);
+  prep.active = active;
+  prep.min_variance = min_variance;
+  prep.lo = clip_lo;
+  prep.hi = clip_hi;
+  return mlp_forward_impl(params, ldp, obs, ldo, out, ldout, N, n_layers, dims_host, acts_host, prep, stream);
 }

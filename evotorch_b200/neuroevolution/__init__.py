@@ -1,3 +1,6 @@
 from .policy import Policy, count_parameters, fill_parameters, parameter_vector
+from .rollout import RolloutResult, rollout
+from .runningnorm import CollectedStats, ObsNormLayer, RunningNorm
 
-__all__ = ["Policy", "count_parameters", "fill_parameters", "parameter_vector"]
+__all__ = ["Policy", "count_parameters", "fill_parameters", "parameter_vector", "RunningNorm", "ObsNormLayer", "CollectedStats", "rollout",
+           "RolloutResult"]

@@ -115,15 +115,30 @@ class Policy:
         return functional_call(self._net, self._unflatten(flat), (x,))
 
     @torch.no_grad()
-    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, *, obs_norm=None, active: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Row i of the parameters applied to observation i (vecrl.py:1240-1279).  Rollout extras, fused into the K8 kernel
+        on CUDA float32: `obs_norm` (a RunningNorm) normalises and clips the observations on the fly, `active` (bool, N)
+        skips the policies of finished sub-environments (zero actions; their parameters are not read)."""
         p = self._parameters
         if p is None:
             raise ValueError("Please use the method `set_parameters(...)` before calling the policy.")
         if p.ndim == 1:
+            if obs_norm is not None:
+                x = obs_norm.normalize(x)
             return self._call_one(p, x)
         if x.ndim != 2 or x.shape[0] != p.shape[0]:
             raise ValueError(f"With {p.shape[0]} parameter rows, expected observations of shape ({p.shape[0]}, ...), got {tuple(x.shape)}")
         if self._spec is not None and ops.uses_kernels(p) and ops.uses_kernels(x) and p.stride(1) == 1 and x.stride(1) == 1:
             dims, acts = self._spec
-            return ops.mlp_forward(p, x, dims, acts)
-        return vmap(self._call_one)(p, x)
+            if obs_norm is None:
+                return ops.mlp_forward(p, x, dims, acts, active=active)
+            if obs_norm.sum is None:
+                raise ValueError("Cannot do normalization because no data is collected yet.")
+            return ops.mlp_forward(p, x, dims, acts, obs_sum=obs_norm.sum, obs_sumsq=obs_norm.sum_of_squares, obs_count=obs_norm.count_tensor,
+                                   min_variance=obs_norm.min_variance, clip=(obs_norm.low, obs_norm.high), active=active)
+        if obs_norm is not None:
+            x = obs_norm.normalize(x)
+        result = vmap(self._call_one)(p, x)
+        if active is not None:
+            result = torch.where(active.reshape((-1,) + (1,) * (result.ndim - 1)), result, torch.zeros_like(result))
+        return result

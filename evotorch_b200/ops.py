@@ -338,8 +338,12 @@ def cem_finalize(s1: torch.Tensor, s2: torch.Tensor, sigma: torch.Tensor, num_el
 ACT_IDS = {"none": 0, "identity": 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 
 
-def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Batched policy forward: row i of `params` (flat Linear-layer parameters) applied to row i of `obs`."""
+def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Optional[torch.Tensor] = None, *,
+                obs_sum: Optional[torch.Tensor] = None, obs_sumsq: Optional[torch.Tensor] = None, obs_count: Optional[torch.Tensor] = None,
+                min_variance: float = 1e-2, clip: Optional[tuple] = None, active: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched policy forward: row i of `params` (flat Linear-layer parameters) applied to row i of `obs`.
+    With `obs_sum / obs_sumsq / obs_count` (the RunningNorm sums, all on the device) the observations are normalised and
+    clipped while they are loaded; with `active` (bool / uint8, N) inactive policies are skipped and get zero actions."""
     import ctypes
 
     _mat(params, "parameters"); _mat(obs, "observations")
@@ -356,10 +360,27 @@ def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Option
     need = nat.lib().evok_mlp_parameter_length(len(act_ids), d_arr)
     if params.shape[1] != need:
         raise ValueError(f"parameters: expected {need} columns for layer widths {dims}, got {params.shape[1]}")
+    if obs_sum is None and active is None:
+        with _timed("mlp_forward"):
+            rc = nat.lib().evok_mlp_forward(params.data_ptr(), params.stride(0), obs.data_ptr(), obs.stride(0), out.data_ptr(), out.stride(0), n,
+                                            len(act_ids), d_arr, a_arr, nat.stream_of(params))
+        nat.check(rc, "evok_mlp_forward")
+        return out
+    if obs_sum is not None:
+        _vec(obs_sum, "obs_sum", dims[0]); _vec(obs_sumsq, "obs_sumsq", dims[0])
+        if obs_count is None or obs_count.dtype != torch.int64 or obs_count.numel() != 1 or not obs_count.is_cuda:
+            raise ValueError("obs_count: expected a 1-element int64 CUDA tensor")
+    if active is not None:
+        if active.dtype == torch.bool:
+            active = active.view(torch.uint8)
+        if active.dtype != torch.uint8 or active.numel() != n or not active.is_cuda or not active.is_contiguous():
+            raise ValueError(f"active: expected {n} contiguous bool / uint8 flags on the GPU")
+    lo, hi = (NAN, NAN) if clip is None else (NAN if clip[0] is None else float(clip[0]), NAN if clip[1] is None else float(clip[1]))
     with _timed("mlp_forward"):
-        rc = nat.lib().evok_mlp_forward(params.data_ptr(), params.stride(0), obs.data_ptr(), obs.stride(0), out.data_ptr(), out.stride(0), n,
-                                        len(act_ids), d_arr, a_arr, nat.stream_of(params))
-    nat.check(rc, "evok_mlp_forward")
+        rc = nat.lib().evok_mlp_forward_prep(params.data_ptr(), params.stride(0), obs.data_ptr(), obs.stride(0), out.data_ptr(), out.stride(0), n,
+                                             len(act_ids), d_arr, a_arr, nat.ptr(obs_sum), nat.ptr(obs_sumsq), nat.ptr(obs_count),
+                                             float(min_variance), lo, hi, nat.ptr(active), nat.stream_of(params))
+    nat.check(rc, "evok_mlp_forward_prep")
     return out
 
 

@@ -186,6 +186,16 @@ int64_t evok_mlp_parameter_length(int n_layers, const int32_t* dims_host);
 int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
                      int n_layers, const int32_t* dims_host, const int32_t* acts_host, void* stream);
 
+/* The same forward with the observation pre-processing of the rollout loop fused into the observation load
+ * (vecgymne.py:604-660, :822-836; net/runningnorm.py:412-533): x = clamp((obs - mean) / stdev, clip_lo, clip_hi), where
+ * mean = obs_sum / count and stdev = sqrt(max(obs_sumsq / count - mean^2, min_variance)) come from the RunningNorm sums on the
+ * device (obs_sum == NULL: no normalisation; clip_* = NaN: no clipping).  `active` (N bytes, nullable): policies whose flag
+ * is 0 are skipped -- their parameters are never read -- and receive zero actions. */
+int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
+                          int n_layers, const int32_t* dims_host, const int32_t* acts_host, const float* obs_sum, const float* obs_sumsq,
+                          const int64_t* obs_count_dev, float min_variance, float clip_lo, float clip_hi, const uint8_t* active,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K6 / K7: fp32-accurate tensor-core GEMM (tcgen05 + TMEM + TMA, 3xTF32 operand splitting).
  *   C[M x N] = A[M x K] * B[N x K]^T        A, B, C row-major fp32 (lda, ldb >= K; ldc >= N)

@@ -1,0 +1,120 @@
+"""RunningNorm, the policy kernel's fused observation normalisation / masking, and the rollout loop."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from evotorch_b200.neuroevolution import ObsNormLayer, Policy, RunningNorm, rollout
+from oracle import rollout_oracle as RO
+from vecenv_fixture import ToyVecEnv
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "runningnorm_golden.npz"))
+DEVICES = ["cpu", pytest.param("cuda", marks=pytest.mark.gpu)]
+
+
+def T(x, device, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device=device)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("tag,clip", [("noclip", None), ("clip", (-1.5, 2.0))])
+def test_running_norm_matches_reference(tag, clip, device):
+    rn = RunningNorm(shape=9, dtype="float32", device=device, min_variance=1e-2, clip=clip)
+    with pytest.raises(ValueError):
+        rn.normalize(T(GOLD["probe"], device))
+    probe = T(GOLD["probe"], device)
+    for i in range(4):
+        mask = GOLD[f"mask{i}"]
+        rn.update(T(GOLD[f"batch{i}"], device), None if mask.all() and i == 0 else T(mask, device, torch.bool))
+        assert rn.count == int(GOLD[f"{tag}/count{i}"])
+        np.testing.assert_allclose(rn.sum.cpu().numpy(), GOLD[f"{tag}/sum{i}"], rtol=2e-6, atol=1e-5)
+        np.testing.assert_allclose(rn.sum_of_squares.cpu().numpy(), GOLD[f"{tag}/sumsq{i}"], rtol=2e-6, atol=1e-4)
+        np.testing.assert_allclose(rn.mean.cpu().numpy(), GOLD[f"{tag}/mean{i}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rn.stdev.cpu().numpy(), GOLD[f"{tag}/stdev{i}"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(rn.normalize(probe).cpu().numpy(), GOLD[f"{tag}/norm{i}"], rtol=2e-4, atol=2e-5)
+    rn.update(T(GOLD["single"], device))
+    assert rn.count == int(GOLD[f"{tag}/count_single"])
+    np.testing.assert_allclose(rn.normalize(probe).cpu().numpy(), GOLD[f"{tag}/norm_single"], rtol=2e-4, atol=2e-5)
+    other = RunningNorm(shape=9, dtype="float32", device=device)
+    other.update(T(GOLD["batch2"], device))
+    rn.update(other)
+    assert rn.count == int(GOLD[f"{tag}/count_merged"])
+    np.testing.assert_allclose(rn.mean.cpu().numpy(), GOLD[f"{tag}/mean_merged"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rn.stdev.cpu().numpy(), GOLD[f"{tag}/stdev_merged"], rtol=2e-5, atol=1e-6)
+    layer = rn.to_layer()
+    assert isinstance(layer, ObsNormLayer)
+    np.testing.assert_allclose(layer(probe).cpu().numpy(), GOLD[f"{tag}/layer"], rtol=2e-4, atol=2e-5)
+    got = rn.update_and_normalize(T(GOLD["batch1"], device), T(GOLD["mask1"], device, torch.bool))
+    np.testing.assert_allclose(got.cpu().numpy(), GOLD[f"{tag}/update_and_normalize"], rtol=2e-4, atol=2e-5)
+    # numpy in -> numpy out; shape and mask validation (runningnorm.py:190-212, :287-307)
+    assert isinstance(rn.normalize(GOLD["probe"]), np.ndarray)
+    with pytest.raises(ValueError):
+        rn.update(torch.zeros(4, 8, device=device))
+    with pytest.raises(ValueError):
+        rn.update(torch.zeros(4, 9, device=device), torch.ones(3, dtype=torch.bool, device=device))
+    with pytest.raises(ValueError):
+        rn.update(torch.zeros(9, device=device), torch.ones(1, dtype=torch.bool, device=device))
+    moved = rn.to("cpu")
+    assert moved.device.type == "cpu" and moved.count == rn.count
+    rn.reset()
+    assert rn.count == 0 and rn.sum is None
+
+
+def _net(n_in, n_hidden, n_out):
+    return nn.Sequential(nn.Linear(n_in, n_hidden), nn.Tanh(), nn.Linear(n_hidden, n_out))
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_policy_call_with_normalisation_and_mask(device):
+    g = np.random.default_rng(2)
+    n, n_in, n_hidden, n_out = 37, 11, 8, 3
+    policy = Policy(_net(n_in, n_hidden, n_out))
+    params = T(g.standard_normal((n, policy.parameter_length)) * 0.3, device)
+    obs = T(g.standard_normal((n, n_in)) * 3 + 1, device)
+    active = T(g.random(n) < 0.7, device, torch.bool)
+    rn = RunningNorm(shape=n_in, dtype="float32", device=device, clip=(-2.0, 2.0))
+    rn.update(obs, active)
+    policy.set_parameters(params)
+    got = policy(obs, obs_norm=rn, active=active)
+    from oracle import es_oracle as O
+
+    ref_norm = RO.RunningNormOracle(n_in, clip=(-2.0, 2.0))
+    ref_norm.update(obs.cpu().numpy()[active.cpu().numpy()])
+    want = O.mlp_policy_forward(params.cpu().numpy(), ref_norm.normalize(obs.cpu().numpy()), n_in, n_hidden, n_out, "tanh")
+    want[~active.cpu().numpy()] = 0.0
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    # mask alone / normalisation alone
+    np.testing.assert_allclose(policy(obs, active=active).cpu().numpy()[active.cpu().numpy()],
+                               policy(obs).cpu().numpy()[active.cpu().numpy()], rtol=0, atol=0)
+    assert torch.count_nonzero(policy(obs, active=active)[~active]) == 0
+    np.testing.assert_allclose(policy(obs, obs_norm=rn).cpu().numpy(), policy(rn.normalize(obs)).cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("variant", ["plain", "normalised", "episodes_bonus_padding"])
+def test_rollout_matches_the_reference_loop(variant, device):
+    g = np.random.default_rng(8)
+    n_in, n_hidden, n_out = 12, 16, 4
+    policy = Policy(_net(n_in, n_hidden, n_out))
+    num_solutions = 50 if variant != "episodes_bonus_padding" else 41
+    num_envs = 50
+    params_np = (g.standard_normal((num_solutions, policy.parameter_length)) * 0.4).astype(np.float32)
+    env = ToyVecEnv(num_envs, n_in, n_out, seed=3, device=device)
+    kw, okw = {}, {}
+    if variant != "plain":
+        kw["obs_norm"] = RunningNorm(shape=n_in, dtype="float32", device=device, clip=(-5.0, 5.0))
+        okw["obs_norm"] = RO.RunningNormOracle(n_in, clip=(-5.0, 5.0))
+    if variant == "episodes_bonus_padding":
+        kw.update(num_episodes=3, decrease_rewards_by=0.25, alive_bonus_schedule=(2, 5, 0.5))
+        okw.update(num_episodes=3, decrease_rewards_by=0.25, alive_bonus_schedule=(2, 5, 0.5))
+    result = rollout(policy, T(params_np, device), env, **kw)
+    want_scores, want_steps = RO.rollout(params_np, n_in, n_hidden, n_out, "tanh", env.as_numpy(), **okw)
+    assert result.interactions == want_steps and result.episodes == num_solutions * kw.get("num_episodes", 1)
+    assert result.scores.shape == (num_solutions,)
+    np.testing.assert_allclose(result.scores.cpu().numpy(), want_scores, rtol=2e-4, atol=2e-4)
+    if "obs_norm" in kw:
+        assert kw["obs_norm"].count == okw["obs_norm"].count
+        np.testing.assert_allclose(kw["obs_norm"].sum.cpu().numpy(), okw["obs_norm"].sum, rtol=1e-4, atol=1e-3)
