@@ -63,5 +63,40 @@ for make in (lambda p: PGPE(p, popsize=64, center_learning_rate=0.5, stdev_learn
             s.enable_cuda_graph()
         s.run(5)
 CMAES(Problem("min", sphere, initial_bounds=(-3, 3), solution_length=40, device=dev, seed=1), stdev_init=1.0, popsize=64).run(3)
+# rollout extras of the policy kernel: fused normalisation / clipping / active mask, masked running statistics
+from evotorch_b200.neuroevolution import RunningNorm  # noqa: E402
+
+for dims, acts, n in (([376, 256, 17], ["tanh", "none"], 9), ([33, 70, 9, 4], ["relu", "sigmoid", "tanh"], 6)):
+    L = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(acts)))
+    obs = torch.randn(n, dims[0], device=dev)
+    active = torch.rand(n, device=dev) < 0.6
+    rn = RunningNorm(shape=dims[0], dtype="float32", device=dev, clip=(-3.0, 3.0))
+    rn.update(obs, active)
+    rn.update(obs)
+    ops.mlp_forward(torch.randn(n, L, device=dev), obs, dims, acts, obs_sum=rn.sum, obs_sumsq=rn.sum_of_squares, obs_count=rn.count_tensor,
+                    clip=(-3.0, 3.0), active=active)
+# lazy population (X = NULL sampler + regenerating gradient) and the peer-exchange kernels (world size 1: same kernels, local "peers")
+s = PGPE(Problem("min", rastrigin, initial_bounds=(-5, 5), solution_length=50, device=dev, seed=1, lazy_population=True), popsize=64,
+         center_learning_rate=0.5, stdev_learning_rate=0.1, stdev_init=1.0)
+s.run(4)
+import tempfile  # noqa: E402
+
+import torch.distributed as dist  # noqa: E402
+
+from evotorch_b200.peer import PeerExchange  # noqa: E402
+
+dist.init_process_group("gloo", init_method=f"file://{tempfile.mkdtemp()}/pg", rank=0, world_size=1)
+n, D = 130, 70
+px = PeerExchange(n, D, torch.device(dev), timeout_ns=2_000_000_000)
+mu, sg = torch.randn(D, device=dev), torch.rand(D, device=dev) + 0.1
+X = torch.empty(n, D, device=dev)
+for gen in range(3):
+    ops.sample_eval_push(2, X, mu, sg, n_rows=n, symmetric=True, seed=3, stream_id=gen, row0=0, peer=px)
+    w = ops.rank(px.wait_fitness(), "centered", False)
+    ops.grad_push(ops.GRAD_SYMMETRIC, X, w, mu, sg, scale_mu=1.0, scale_sigma=1.0, peer=px)
+    px.reduce_gradients()
+    ops.grad_push(ops.GRAD_SYMMETRIC, None, w, mu, sg, scale_mu=1.0, scale_sigma=1.0, peer=px, seed=3, stream_id=gen, row0=0)
+    px.reduce_gradients()
+assert not px.timed_out()
 torch.cuda.synchronize()
 print("SANITIZE_RUN_COMPLETE")
