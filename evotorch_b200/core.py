@@ -377,7 +377,12 @@ class Problem:
     def _finish_evaluation(self, batch: "SolutionBatch"):
         self._after_eval_status = {}
         self._after_eval_status.update(self._get_best_and_worst(batch))
+        self._after_eval_status.update(self._extra_status(batch))
         self._after_eval_status.update(self._after_eval_hook.accumulate_dict(batch))
+
+    def _extra_status(self, batch: "SolutionBatch") -> dict:
+        """Override point: problem-specific status items (core.py `_extra_status`)."""
+        return {}
 
     def _evaluate_batch(self, batch: "SolutionBatch"):
         """Override point (core.py:2602-2611).  Built-in objectives run the K2 row-reduction kernel."""

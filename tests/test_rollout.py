@@ -118,3 +118,52 @@ def test_rollout_matches_the_reference_loop(variant, device):
     if "obs_norm" in kw:
         assert kw["obs_norm"].count == okw["obs_norm"].count
         np.testing.assert_allclose(kw["obs_norm"].sum.cpu().numpy(), okw["obs_norm"].sum, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_vecne_problem_drives_pgpe(device):
+    """The neuroevolution problem class on top of the rollout loop (VecGymNE's evaluation side): PGPE improves the return,
+    the counters and the observation statistics advance, sub-batching by `max_num_envs` gives the same scores, and the
+    exported policy reproduces the batched kernel's actions."""
+    from evotorch_b200.algorithms import PGPE
+    from evotorch_b200.neuroevolution import VecNE
+    from evotorch_b200 import SolutionBatch
+
+    n_in, n_out = 10, 3
+    make_env = lambda num_envs, **kw: ToyVecEnv(num_envs, n_in, n_out, device=device, **kw)  # noqa: E731
+    prob = VecNE(make_env, _net(n_in, 12, n_out), env_config=dict(seed=5), observation_normalization=True, num_episodes=2,
+                 decrease_rewards_by=0.1, device=device, seed=7)
+    assert prob.solution_length == n_in * 12 + 12 + 12 * n_out + n_out and prob.senses == ["max"]
+    searcher = PGPE(prob, popsize=64, center_learning_rate=0.05, stdev_learning_rate=0.1, stdev_init=0.1)
+    searcher.step()
+    first = searcher.status["mean_eval"]
+    assert searcher.status["total_episode_count"] == 128 and searcher.status["total_interaction_count"] > 128
+    searcher.run(25)
+    assert searcher.status["mean_eval"] > first + 1.0
+    stats = prob.get_observation_stats()
+    assert stats.count == searcher.status["total_interaction_count"] and prob.pop_observation_stats().count == stats.count
+    assert prob.pop_observation_stats() is None
+
+    # same solutions, evaluated in sub-batches of at most 20 environments (fresh problems: the statistics start equal)
+    def scores(max_envs):
+        p = VecNE(make_env, _net(n_in, 12, n_out), env_config=dict(seed=5), max_num_envs=max_envs, device=device, seed=7)
+        batch = SolutionBatch(p, popsize=50, empty=True)
+        batch.set_values(searcher.population.values[:50].clone())
+        p.evaluate(batch)
+        return batch.evals.clone().view(-1)
+
+    whole, pieces = scores(None), scores(20)
+    # 50 solutions in pieces of <= 20 -> 17 + 17 + 16; sub-environment i has its own start state and episode length, so only the
+    # first piece meets the same environments as the unsplit evaluation
+    torch.testing.assert_close(pieces[:17], whole[:17], rtol=1e-5, atol=1e-5)
+    assert not torch.allclose(pieces[17:34], whole[17:34])
+
+    center = searcher.status["center"]
+    module = prob.to_policy(center)
+    obs = torch.randn(4, n_in)
+    pol = Policy(_net(n_in, 12, n_out))
+    pol.set_parameters(center.cpu().expand(4, -1).contiguous())
+    want = pol(obs, obs_norm=stats.to("cpu"))
+    torch.testing.assert_close(module(obs), want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        VecNE(make_env, _net(n_in, 12, n_out), device=device).get_observation_stats()
