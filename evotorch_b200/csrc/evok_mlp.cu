@@ -35,7 +35,11 @@ struct ObsPrep {
   const long long* count;  // number of observations behind the sums (device scalar)
   const unsigned char* active;  // N flags, nullptr = all active
   float min_variance, lo, hi;   // lo / hi = NaN: no clipping on that side
+  unsigned int* ticket;         // zeroed work counter (nullptr: static round-robin).  With a mask the number of active policies per
+                                // CTA is binomial under round-robin (1.9x imbalance at 10 % active); CTAs then draw chunks of rows
 };
+
+constexpr int kMlpTicketRows = 4;  // rows per ticket: 1/4 of the atomics, balance to within 4 rows
 
 __device__ __forceinline__ float prep_obs(const ObsPrep& p, int k, float o) {
   if (!p.sum) return o;
@@ -73,7 +77,30 @@ __global__ void __launch_bounds__(kMlpThreads)
   extern __shared__ __align__(16) float act_buf[];  // 2 x (max_width + 2 * kMlpPad)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stride = (spec.max_width + 2 * kMlpPad + 3) & ~3;  // keeps both ping-pong buffers 16-byte aligned
-  for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+  __shared__ unsigned int next_chunk;
+  const bool dynamic = prep.ticket != nullptr;
+  int64_t i = dynamic ? 0 : (int64_t)blockIdx.x - gridDim.x;
+  int in_chunk = kMlpTicketRows;  // forces a ticket draw on the first iteration
+  for (;;) {
+    if (dynamic) {
+      if (in_chunk == kMlpTicketRows) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_chunk = atomicAdd(prep.ticket, 1u);
+        __syncthreads();
+        i = (int64_t)next_chunk * kMlpTicketRows;
+        in_chunk = 0;
+      } else {
+        ++i;
+      }
+      ++in_chunk;
+      if (i >= N) {
+        if (in_chunk == 1) break;  // the chunk starts beyond the end: no work left anywhere
+        continue;                  // tail of the last chunk
+      }
+    } else {
+      i += gridDim.x;
+      if (i >= N) break;
+    }
     if (prep.active && !prep.active[i]) {  // CTA-uniform: the whole policy is skipped
       for (int k = threadIdx.x; k < spec.dims[spec.n_layers]; k += kMlpThreads) out[i * ldout + k] = 0.0f;
       continue;
@@ -198,7 +225,7 @@ extern "C" EVOK_API int evok_mlp_forward(const float* params, int64_t ldp, const
 extern "C" EVOK_API int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
                                               int n_layers, const int32_t* dims_host, const int32_t* acts_host, const float* obs_sum,
                                               const float* obs_sumsq, const int64_t* obs_count_dev, float min_variance, float clip_lo, float clip_hi,
-                                              const uint8_t* active, void* stream) {
+                                              const uint8_t* active, void* ws, size_t ws_bytes, void* stream) {
   if ((obs_sum != nullptr) != (obs_sumsq != nullptr) || (obs_sum != nullptr) != (obs_count_dev != nullptr)) return EVOK_E_NULLPTR;
   ObsPrep prep{};
   prep.sum = obs_sum;
@@ -208,5 +235,10 @@ extern "C" EVOK_API int evok_mlp_forward_prep(const float* params, int64_t ldp, 
   prep.min_variance = min_variance;
   prep.lo = clip_lo;
   prep.hi = clip_hi;
+  if (active && ws && ws_bytes >= sizeof(unsigned int) && N > 0) {  // masked: balance the surviving policies over the CTAs dynamically
+    prep.ticket = static_cast<unsigned int*>(ws);
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   return mlp_forward_impl(params, ldp, obs, ldo, out, ldout, N, n_layers, dims_host, acts_host, prep, stream);
 }

@@ -375,11 +375,13 @@ def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Option
             active = active.view(torch.uint8)
         if active.dtype != torch.uint8 or active.numel() != n or not active.is_cuda or not active.is_contiguous():
             raise ValueError(f"active: expected {n} contiguous bool / uint8 flags on the GPU")
+    ws = None if active is None else nat.workspace(params.device, 256, "mlp")
     lo, hi = (NAN, NAN) if clip is None else (NAN if clip[0] is None else float(clip[0]), NAN if clip[1] is None else float(clip[1]))
     with _timed("mlp_forward"):
         rc = nat.lib().evok_mlp_forward_prep(params.data_ptr(), params.stride(0), obs.data_ptr(), obs.stride(0), out.data_ptr(), out.stride(0), n,
                                              len(act_ids), d_arr, a_arr, nat.ptr(obs_sum), nat.ptr(obs_sumsq), nat.ptr(obs_count),
-                                             float(min_variance), lo, hi, nat.ptr(active), nat.stream_of(params))
+                                             float(min_variance), lo, hi, nat.ptr(active), nat.ptr(ws), 0 if ws is None else ws.numel(),
+                                             nat.stream_of(params))
     nat.check(rc, "evok_mlp_forward_prep")
     return out
 

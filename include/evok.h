@@ -190,11 +190,13 @@ int evok_mlp_forward(const float* params, int64_t ldp, const float* obs, int64_t
  * (vecgymne.py:604-660, :822-836; net/runningnorm.py:412-533): x = clamp((obs - mean) / stdev, clip_lo, clip_hi), where
  * mean = obs_sum / count and stdev = sqrt(max(obs_sumsq / count - mean^2, min_variance)) come from the RunningNorm sums on the
  * device (obs_sum == NULL: no normalisation; clip_* = NaN: no clipping).  `active` (N bytes, nullable): policies whose flag
- * is 0 are skipped -- their parameters are never read -- and receive zero actions. */
+ * is 0 are skipped -- their parameters are never read -- and receive zero actions.  `ws` (nullable, >= 4 bytes, 4-byte aligned):
+ * with a mask, CTAs draw row chunks from a work counter kept there instead of a static round-robin (which leaves the number of
+ * surviving policies per CTA binomially unbalanced). */
 int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, int64_t ldo, float* out, int64_t ldout, int64_t N,
                           int n_layers, const int32_t* dims_host, const int32_t* acts_host, const float* obs_sum, const float* obs_sumsq,
                           const int64_t* obs_count_dev, float min_variance, float clip_lo, float clip_hi, const uint8_t* active,
-                          void* stream);
+                          void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6 / K7: fp32-accurate tensor-core GEMM (tcgen05 + TMEM + TMA, 3xTF32 operand splitting).
