@@ -137,6 +137,11 @@ class ClockSampler:
                                           "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi takes a moment to start (NVML initialisation over all GPUs of the box, during which driver calls of this process
+            # can stall): wait for its first sample so that none of that falls into the timed region
+            deadline = time.perf_counter() + 5.0
+            while not self.lines and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -233,8 +238,8 @@ def run_ours(args):
         searcher.step()
 
     # ---- device-resident timing (value) + live per-kernel timing (roofline)
+    clocks = ClockSampler(local_rank) if rank == 0 else None  # started (and warmed up) BEFORE the barrier: rank 0 must not enter late
     barrier_sync()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ops.launch_count()
     ops.enable_timers()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
