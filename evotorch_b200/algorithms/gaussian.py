@@ -235,6 +235,14 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         once and replayed.  NOTE: replayed collectives run on the replaying stream, eager ones on NCCL's internal stream; do not
         interleave a graph-mode searcher with other collectives on the same process group without a device synchronisation."""
         prob = self.problem
+        if os.environ.get("EVOTORCH_B200_PEER", "0") == "1" and getattr(prob, "_peer_exchange", None) is None and not self.__dict__.get("_peer_tried"):
+            # opt-in by environment: fuse the two exchanges of the generation into the producing kernels (evotorch_b200/peer.py)
+            self._peer_tried = True
+            from ..distributed import world
+            from ..peer import enable_peer_exchange
+
+            if world()[1] > 1 and ops.uses_kernels(self._distribution.mu) and prob.evok_objective_id is not None and prob.rng == "philox":
+                enable_peer_exchange(prob, self._popsize)
         if not (self._use_graph and self._graph_capturable()):
             self._graph = None
             self._distributed_body(in_place=False)

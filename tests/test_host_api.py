@@ -357,3 +357,24 @@ def test_pickling_logger_files_items_and_resume(tmp_path, capsys):
     with pytest.raises(KeyError):
         lg = PicklingLogger(s, interval=1, directory=str(tmp_path / "plain"), prefix="p", verbose=False)
         PicklingLogger.resume(lg.save())
+
+
+def test_lazy_population_and_peer_exchange_fail_loudly_without_their_prerequisites():
+    """Neither feature has a CPU stand-in: a lazy population needs the fused Philox sampler (CUDA float32 + built-in objective),
+    a peer exchange needs an initialised process group."""
+    from evotorch_b200.core import LazySolutionBatch
+    from evotorch_b200.objectives import rastrigin as builtin_rastrigin
+    from evotorch_b200.peer import PeerExchange
+
+    prob = Problem("min", builtin_rastrigin, initial_bounds=(-1, 1), solution_length=8, lazy_population=True, seed=1)
+    searcher = SNES(prob, popsize=10, stdev_init=1.0)
+    with pytest.raises(ValueError, match="lazy population"):
+        searcher.step()
+    batch = LazySolutionBatch(prob, 10)
+    assert len(batch) == 10 and batch.values_shape == (10, 8) and "LazySolutionBatch" in repr(batch)
+    with pytest.raises(ValueError):
+        batch.values  # not sampled yet
+    with pytest.raises(ValueError):
+        batch.set_values(torch.zeros(10, 8))
+    with pytest.raises(RuntimeError, match="process group"):
+        PeerExchange(10, 8, torch.device("cpu"))
