@@ -86,10 +86,15 @@ inline PhiloxKey make_philox_key(uint64_t seed, uint64_t stream_id) {
   return k;
 }
 
+// EVOK_PHILOX_ROUNDS exists for MEASUREMENT builds only (scripts/build_variants.py: what would fewer rounds buy?); the
+// product is Philox4x32-10, the variant cuRAND / torch use, and the oracle restates exactly that.
+#ifndef EVOK_PHILOX_ROUNDS
+#define EVOK_PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKey& key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < EVOK_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     U4 n;

@@ -15,6 +15,9 @@ VARIANTS = {
     "gt_r6_s3_c3": ("EVOK_GRAD_TMA_ROWS=6", "EVOK_GRAD_TMA_STAGES=3", "EVOK_GRAD_TMA_CTAS_PER_SM=3"),
     "so_unr1_minb6": ("EVOK_SAMPLEONLY_UNR=1", "EVOK_SAMPLEONLY_MINB=6"),
     "so_unr2_minb4": ("EVOK_SAMPLEONLY_UNR=2", "EVOK_SAMPLEONLY_MINB=4"),
+    # measurement only: how much of the fused sampler is the counter-based RNG?  (never shipped: the product is Philox4x32-10)
+    "philox7": ("EVOK_PHILOX_ROUNDS=7",),
+    "philox4": ("EVOK_PHILOX_ROUNDS=4",),
 }
 only = sys.argv[1:]
 for tag, defs in VARIANTS.items():

@@ -58,7 +58,7 @@ for path in libs:
     h = load(path)
 
     def sample(obj=2, store=True):
-        rc = h.evok_sample_eval(obj, X.data_ptr() if store else None, D, mu.data_ptr(), sg.data_ptr(), 0, N, D, 1, 7, 1,
+        rc = h.evok_sample_eval(obj, X.data_ptr() if store else None, D, mu.data_ptr(), sg.data_ptr(), 0, N, D, 1, 7, 1, None,
                                 f.data_ptr() if obj else None, stream)
         assert rc == 0, rc
 
@@ -71,6 +71,8 @@ for path in libs:
     t_s = timeit(lambda: sample(0, True))
     t_lazy = timeit(lambda: sample(2, False))
     t_g = timeit(grad)
+    t_rng = timeit(lambda: sample(1, False))       # sphere, no store: Philox + Box-Muller + one FFMA per element = the RNG floor
+    t_sphere = timeit(lambda: sample(1, True))     # sphere with the store
     sample(2, True)
     grad()
     torch.cuda.synchronize()
@@ -80,9 +82,9 @@ for path in libs:
     gdiff = float((cur - ref_g).abs().max() / ref_g.abs().max())
     gb = 4.0 * N * D / 1e9
     results[tag] = {"sample_eval_ms": t_se, "sample_eval_gbs": gb / t_se * 1e3, "sample_only_ms": t_s, "sample_only_gbs": gb / t_s * 1e3,
-                    "lazy_eval_ms": t_lazy, "grad_ms": t_g, "grad_gbs": 0.5 * gb / t_g * 1e3}
+                    "lazy_eval_ms": t_lazy, "rng_only_ms": t_rng, "sphere_store_ms": t_sphere, "grad_ms": t_g, "grad_gbs": 0.5 * gb / t_g * 1e3}
     print(f"{tag:28s} sample_eval {t_se:7.3f} ms {gb / t_se * 1e3:7.0f} GB/s | sample {t_s:7.3f} ms {gb / t_s * 1e3:7.0f} GB/s | "
-          f"lazy {t_lazy:7.3f} ms | grad {t_g:7.3f} ms {0.5 * gb / t_g * 1e3:7.0f} GB/s (rel diff vs default {gdiff:.1e})", flush=True)
+          f"lazy {t_lazy:7.3f} ms | rng-only {t_rng:7.3f} ms | sphere+store {t_sphere:7.3f} ms | grad {t_g:7.3f} ms {0.5 * gb / t_g * 1e3:7.0f} GB/s (rel diff vs default {gdiff:.1e})", flush=True)
 # K8 at BASELINE config 4: 65 536 policies x 100 881 parameters (26.4 GB), one observation each
 del X, f, w
 torch.cuda.empty_cache()
