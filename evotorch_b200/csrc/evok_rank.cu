@@ -244,6 +244,104 @@ __global__ void __launch_bounds__(256) elite_mask_kernel(const uint32_t* __restr
   if (p < N) mask[idx[p]] = p < num_elites ? 1.0f : 0.0f;
 }
 
+// ---- small populations: rank by counting, ONE launch -------------------------------------------------
+// For N <= kSmallRankMax the 14-launch radix pipeline is pure launch latency (about 60 us inside a CUDA graph, more in eager
+// mode), while the stable rank of element i is simply  #{j : key_j < key_i} + #{j < i : key_j == key_i}.  All N^2 comparisons
+// (67 M at N = 8192) spread over the whole GPU take a few microseconds: 4 lanes share one element (interleaved quarters of
+// the key tile staged in shared memory: conflict-free, broadcast reads; 8 or 16 lanes for larger N, so that the grid always
+// covers the GPU), 256 / lanes elements per CTA.  The utility (or the elite flag,
+// or the permutation entry) is written by the same kernel, so make_keys + 12 sort launches + the scatter collapse into one.
+constexpr int kSmallRankMax = 8192;
+constexpr int kSmallThreads = 256;
+constexpr int kSmallTile = 2048;
+
+enum { kSmallUtilities = 0, kSmallArgsort = 1, kSmallEliteMask = 2 };
+
+template <int PARTS>
+__global__ void __launch_bounds__(kSmallThreads)
+    rank_small_kernel(const float* __restrict__ f, int N, int descending, int mode, int method, int64_t num_elites, float* __restrict__ out,
+                      int64_t* __restrict__ perm) {
+  __shared__ uint32_t tile[kSmallTile];
+  __shared__ double red[33];
+  constexpr int kElems = kSmallThreads / PARTS;
+  const int part = threadIdx.x % PARTS;
+  const int i = blockIdx.x * kElems + threadIdx.x / PARTS;
+  uint32_t ki = 0;
+  if (i < N) {
+    ki = orderable(f[i]);
+    if (descending) ki = ~ki;
+  }
+  uint32_t cnt = 0;
+  for (int base = 0; base < N; base += kSmallTile) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < kSmallTile; t += kSmallThreads) {
+      const int j = base + t;
+      uint32_t k = 0xFFFFFFFFu;  // padding: never below a real key, and never "equal with a lower index"
+      if (j < N) {
+        k = orderable(f[j]);
+        if (descending) k = ~k;
+      }
+      tile[t] = k;
+    }
+    __syncthreads();
+    const int lim = min(kSmallTile, N - base);
+#pragma unroll 4
+    for (int t = part; t < lim; t += PARTS) {
+      const uint32_t k = tile[t];
+      cnt += (uint32_t)(k < ki) + (uint32_t)((k == ki) & (base + t < i));
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < PARTS; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+
+  float nes_sum = 0.0f;
+  if (mode == kSmallUtilities && method == EVOK_RANK_NES) {  // the table sum of nes_table_sum_kernel, once per CTA
+    const float Nf = (float)N, top = logf(Nf / 2.0f + 1.0f);
+    double acc = 0.0;
+    for (int p = threadIdx.x; p < N; p += kSmallThreads) acc += (double)fmaxf(0.0f, top - logf(Nf - (float)p));
+    nes_sum = (float)block_sum<double>(acc, red);
+  }
+  if (i >= N || part != 0) return;
+  const uint32_t p = cnt;  // position in sorted order
+  if (perm) perm[p] = (int64_t)i;
+  if (mode == kSmallUtilities) {
+    float u;
+    if (method == EVOK_RANK_CENTERED) {
+      u = __fdiv_rn((float)p, (float)(N - 1)) - 0.5f;
+    } else if (method == EVOK_RANK_LINEAR) {
+      u = __fdiv_rn((float)p, (float)(N - 1));
+    } else {
+      const float Nf = (float)N;
+      const float t = fmaxf(0.0f, logf(Nf / 2.0f + 1.0f) - logf(Nf - (float)p));
+      u = __fdiv_rn(t, nes_sum) - __fdiv_rn(1.0f, Nf);
+    }
+    out[i] = u;
+  } else if (mode == kSmallEliteMask) {
+    out[i] = (int64_t)p < num_elites ? 1.0f : 0.0f;
+  }
+}
+
+static int rank_small(const float* f, int64_t N, int descending, int mode, int method, int64_t num_elites, float* out, int64_t* perm, cudaStream_t st) {
+  // lanes per element grow with N: the work per thread stays <= 512 comparisons and the grid >= N / 64 CTAs
+  if (N <= 1024) {
+    rank_small_kernel<4><<<(unsigned)((N + 63) / 64), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+  } else if (N <= 4096) {
+    rank_small_kernel<8><<<(unsigned)((N + 31) / 32), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+  } else {
+    rank_small_kernel<16><<<(unsigned)((N + 15) / 16), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+  }
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+static bool use_small_rank(int64_t N) {
+  static const int enabled = [] {
+    const char* e = getenv("EVOK_RANK_SMALL");
+    return e ? atoi(e) : 1;
+  }();
+  return enabled && N <= kSmallRankMax;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 struct SortPlan {
   int64_t N;
@@ -316,6 +414,7 @@ extern "C" EVOK_API int evok_rank(int method, const float* f, int64_t N, int hig
     if (method == EVOK_RANK_NORMALIZED) mean_std_kernel<<<1, 1024, 0, st>>>(f, N, sign, scalar);
     affine_kernel<<<nb, 256, 0, st>>>(f, N, sign, scalar, method == EVOK_RANK_NORMALIZED, w);
     EVOK_CHECK_LAUNCH_N(method == EVOK_RANK_NORMALIZED ? 2 : 1);
+    if (perm && use_small_rank(N)) return rank_small(f, N, !higher_is_better, kSmallArgsort, 0, 0, nullptr, perm, st);
     if (perm) {
       uint32_t* sidx = nullptr;
       int rc = sort_pairs(f, N, !higher_is_better, ws, p, st, &sidx);
@@ -325,6 +424,7 @@ extern "C" EVOK_API int evok_rank(int method, const float* f, int64_t N, int hig
     }
     return 0;
   }
+  if (use_small_rank(N)) return rank_small(f, N, !higher_is_better, kSmallUtilities, method, 0, w, perm, st);
   uint32_t* sidx = nullptr;
   int rc = sort_pairs(f, N, !higher_is_better, ws, p, st, &sidx);
   if (rc) return rc;
@@ -341,6 +441,7 @@ extern "C" EVOK_API int evok_argsort(const float* keys, int64_t N, int descendin
   const SortPlan p = make_plan(N);
   if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_small_rank(N)) return rank_small(keys, N, descending, kSmallArgsort, 0, 0, nullptr, perm, st);
   uint32_t* sidx = nullptr;
   int rc = sort_pairs(keys, N, descending, ws, p, st, &sidx);
   if (rc) return rc;
@@ -366,6 +467,7 @@ extern "C" EVOK_API int evok_elite_mask(const float* w, int64_t N, int64_t num_e
   const SortPlan p = make_plan(N);
   if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_small_rank(N)) return rank_small(w, N, /*descending=*/1, kSmallEliteMask, 0, num_elites, mask, nullptr, st);
   uint32_t* sidx = nullptr;
   int rc = sort_pairs(w, N, /*descending=*/1, ws, p, st, &sidx);
   if (rc) return rc;

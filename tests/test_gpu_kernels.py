@@ -174,7 +174,7 @@ def test_rank_matches_reference_golden(golden, name, method, hib):
     np.testing.assert_array_equal(N(perm), O.argsort_for_ranking(f, hib))  # bit-exact ranking indices
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 2048, 2049, 100_003, 1_000_000])
+@pytest.mark.parametrize("n", [1, 2, 31, 1024, 1025, 2049, 4096, 4097, 8192, 8193, 100_003, 1_000_000])  # <= 8192: the single-launch counting rank; above: radix
 @pytest.mark.parametrize("hib", [True, False])
 def test_rank_large_with_ties_nan_and_signed_zero(n, hib):
     rng = np.random.default_rng(n)
@@ -218,6 +218,13 @@ def test_rank_properties_and_helpers():
     wt = torch.tensor([1.0, 5.0, 5.0, 2.0, 5.0, 0.0], device=DEV)
     assert ops.elite_mask(wt, 2).tolist() == [0, 1, 1, 0, 0, 0]
     assert ops.elite_mask(wt, 4).tolist() == [0, 1, 1, 1, 1, 0]
+    # the counting path (n <= 8192) and the radix path (n > 8192) agree with torch on both sides of the switch
+    for m in (5000, 8192, 8193, 20000):
+        wm = torch.randn(m, device=DEV).round(decimals=1)  # plenty of ties
+        ref = torch.zeros(m, device=DEV)
+        ref[torch.argsort(wm, descending=True, stable=True)[: m // 3]] = 1
+        assert torch.equal(ops.elite_mask(wm, m // 3), ref), m
+        assert torch.equal(ops.argsort(wm, descending=False), torch.argsort(wm, stable=True)), m
     with pytest.raises(KeyError):
         ops.rank(f, "nope", True)
 
