@@ -18,7 +18,7 @@ from typing import Any, Callable, Iterable, Optional, Union
 import torch
 
 from . import ops
-from .tools.misc import ensure_tensor_length_and_dtype, make_gaussian, make_uniform, to_torch_dtype
+from .tools.misc import ensure_tensor_length_and_dtype, extract_generator, make_gaussian, make_uniform, to_torch_dtype
 
 ObjectiveSense = Union[str, Iterable[str]]
 
@@ -240,6 +240,27 @@ class Problem:
         return self._after_eval_hook
 
     @property
+    def before_grad_hook(self) -> Hook:
+        """Called (no arguments) at the start of `sample_and_compute_gradients` (core.py:2204, :2889)."""
+        return self.__dict__.setdefault("_before_grad_hook", Hook())
+
+    @property
+    def after_grad_hook(self) -> Hook:
+        """Called with the list of result dictionaries of `sample_and_compute_gradients`; dictionaries it returns are
+        merged into the problem's status (core.py:2212, :3070)."""
+        return self.__dict__.setdefault("_after_grad_hook", Hook())
+
+    def is_on_cpu(self) -> bool:
+        return str(self._device) == "cpu"
+
+    def kill_actors(self):
+        """No-op: there are no Ray actors here (one process per GPU replaces them, distributed.py)."""
+
+    @property
+    def all_remote_problems(self):
+        raise NotImplementedError("Ray actors are out of scope: shard the population over GPUs with torchrun (evotorch_b200/distributed.py)")
+
+    @property
     def status(self) -> dict:
         return self._after_eval_status
 
@@ -302,6 +323,20 @@ class Problem:
         if out is None:
             out = self.make_empty(*size, num_solutions=num_solutions, dtype=dtype, device=device)
         return make_uniform(out=out, lb=lb, ub=ub, generator=self._generator if generator is None else generator)
+
+    def make_randint(self, *size, n, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False,
+                     generator=None) -> torch.Tensor:
+        """Uniform random integers in [0, n-1], as integers or as floats (tools/tensormaker.py:681-749)."""
+        if out is None:
+            dt, dev = self._tm(dtype, device, use_eval_dtype)
+            out = torch.empty(self._size(size, num_solutions), dtype=dt, device=dev)
+        gen = extract_generator(self._generator if generator is None else generator)
+        n = int(n)
+        if out.dtype.is_floating_point:
+            out.copy_(torch.randint(0, n, out.shape, generator=gen, device=out.device, dtype=torch.int64))
+        else:
+            out.random_(0, n, generator=gen)
+        return out
 
     def ensure_tensor_length_and_dtype(self, t: Any, *, allow_scalar: bool = False, about: Optional[str] = None) -> torch.Tensor:
         return ensure_tensor_length_and_dtype(t, self._solution_length, self._dtype, about=about, allow_scalar=allow_scalar,
@@ -517,7 +552,12 @@ class Problem:
         if ensure_even_popsize and popsize % 2 != 0:
             popsize += 1
         obj_index = self.normalize_obj_index(obj_index)
+        hooks = self.__dict__
+        if len(hooks.get("_before_grad_hook", ())) >= 1:
+            hooks["_before_grad_hook"]()
         result = sharded_sample_and_gradients(self, distribution, popsize, obj_index=obj_index, ranking_method=ranking_method)
+        if len(hooks.get("_after_grad_hook", ())) >= 1:
+            self._after_eval_status = hooks["_after_grad_hook"].accumulate_dict([result])
         return [result] if with_stats else result["gradients"]
 
     def compare_solutions(self, a: "Solution", b: "Solution", obj_index: Optional[int] = None) -> float:
@@ -725,6 +765,10 @@ class SolutionBatch:
 
         keys, is_max = self._sort_keys(obj_index)
         return rank(keys, "raw" if ranking_method is None else ranking_method, higher_is_better=is_max)
+
+    def utils(self, *, ranking_method: Optional[str] = None) -> torch.Tensor:
+        """Utilities for every objective, shape (N, number of objectives) (core.py:4304-4346)."""
+        return torch.stack([self.utility(i, ranking_method=ranking_method) for i in range(self._num_objs)], dim=1)
 
     # ------------------------------------------------------------------ restructuring
     def take(self, indices: Iterable) -> "SolutionBatch":

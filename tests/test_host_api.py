@@ -378,3 +378,27 @@ def test_lazy_population_and_peer_exchange_fail_loudly_without_their_prerequisit
         batch.set_values(torch.zeros(10, 8))
     with pytest.raises(RuntimeError, match="process group"):
         PeerExchange(10, 8, torch.device("cpu"))
+
+
+def test_gradient_hooks_randint_and_misc_problem_api():
+    """core.py:2204-2226 (before / after grad hooks around sample_and_compute_gradients), tensormaker.py:681 (make_randint),
+    core.py:3303 (is_on_cpu), core.py:4304 (SolutionBatch.utils)."""
+    prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=6, vectorized=True, seed=2)
+    calls = []
+    prob.before_grad_hook.append(lambda: calls.append("before"))
+    prob.after_grad_hook.append(lambda results: {"grad_calls": len(calls), "n": results[0]["num_solutions"]})
+    dist = SymmetricSeparableGaussian({"mu": torch.zeros(6), "sigma": torch.ones(6), "divide_mu_grad_by": "num_directions",
+                                       "divide_sigma_grad_by": "num_directions"})
+    out = prob.sample_and_compute_gradients(dist, 20, ranking_method="centered")
+    assert calls == ["before"] and prob.status == {"grad_calls": 1, "n": 20} and set(out[0]["gradients"]) == {"mu", "sigma"}
+    assert prob.is_on_cpu() and prob.kill_actors() is None
+    with pytest.raises(NotImplementedError):
+        prob.all_remote_problems
+    r = prob.make_randint(1000, n=7)
+    assert r.dtype == prob.dtype and r.min() >= 0 and r.max() <= 6 and set(r.tolist()) == set(range(7))
+    ri = prob.make_randint(5, 3, n=4, dtype=torch.int64)
+    assert ri.shape == (5, 3) and ri.dtype == torch.int64 and int(ri.max()) < 4
+    batch = SolutionBatch(prob, popsize=9)
+    prob.evaluate(batch)
+    u = batch.utils(ranking_method="centered")
+    assert u.shape == (9, 1) and torch.equal(u[:, 0], batch.utility(0, ranking_method="centered"))
