@@ -134,7 +134,8 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
               and prob.evok_objective_id is not None and len(prob.senses) == 1 and prob.eval_data_length == 0
               and (self._optimizer is None or isinstance(self._optimizer, ClipUp)))
         if self._distributed:  # the sharded generation has no Python between its kernels / collectives either
-            return ok and not prob.stores_solution_stats and len(prob.before_eval_hook) == 0 and len(prob.after_eval_hook) == 0
+            return (ok and not prob.stores_solution_stats and len(prob.before_eval_hook) == 0 and len(prob.after_eval_hook) == 0
+                    and len(prob.before_grad_hook) == 0 and len(prob.after_grad_hook) == 0)  # Python hooks do not replay
         return ok and self._population is not None
 
     def _update_in_place(self, gradients: dict):
