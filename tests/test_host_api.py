@@ -402,3 +402,67 @@ def test_gradient_hooks_randint_and_misc_problem_api():
     prob.evaluate(batch)
     u = batch.utils(ranking_method="centered")
     assert u.shape == (9, 1) and torch.equal(u[:, 0], batch.utility(0, ranking_method="centered"))
+
+
+def _shifted_to_maximise(x):
+    return -torch.sum((x - 1.5) ** 2 * torch.arange(1, x.shape[-1] + 1, dtype=x.dtype), dim=-1)
+
+
+@pytest.mark.parametrize("tag", ["separable", "no_active", "csa_squared_bounds", "maximise_default_popsize", "ratios_no_limit"])
+def test_cmaes_option_variants_match_reference(tag):
+    """Every CMA-ES option of the reference (cmaes.py:90-606): separable covariance, no active weights, squared CSA with
+    step-size bounds, maximisation with the default population size, hyper-parameter ratios without the decomposition limit.
+    Same seed -> same torch-generator stream on CPU, so the trajectories are compared step by step."""
+    import os
+
+    from evotorch_b200.algorithms import CMAES
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cmaes_variants_golden.npz"))
+    cfg = {
+        "separable": ("min", sphere, 8, dict(stdev_init=1.0, popsize=14, separable=True)),
+        "no_active": ("min", sphere, 6, dict(stdev_init=0.7, popsize=10, active=False)),
+        "csa_squared_bounds": ("min", sphere, 6, dict(stdev_init=1.0, popsize=12, csa_squared=True, stdev_min=0.6, stdev_max=1.1)),
+        "maximise_default_popsize": ("max", _shifted_to_maximise, 7, dict(stdev_init=2.0)),
+        "ratios_no_limit": ("min", sphere, 5, dict(stdev_init=1.0, popsize=16, c_1_ratio=0.5, c_mu_ratio=2.0, c_sigma_ratio=1.5, damp_sigma_ratio=0.8,
+                                                   c_c_ratio=1.2, c_m=0.9, limit_C_decomposition=False)),
+    }[tag]
+    sense, fn, d, kw = cfg
+    prob = Problem(sense, fn, initial_bounds=(-3, 3), solution_length=d, vectorized=True, seed=11, dtype=torch.float32)
+    c = CMAES(prob, **kw)
+    assert c.popsize == int(gold[f"{tag}/popsize"])
+    for t in range(7):
+        c.step()
+        np.testing.assert_allclose(c.population.evals[:, 0].numpy(), gold[f"{tag}/f"][t], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(c.m.numpy(), gold[f"{tag}/m"][t], rtol=2e-5, atol=5e-6)
+        np.testing.assert_allclose(float(c.sigma), float(gold[f"{tag}/sigma"][t]), rtol=2e-5)
+        np.testing.assert_allclose(c.C.numpy(), gold[f"{tag}/C"][t], rtol=5e-5, atol=5e-6)
+        np.testing.assert_allclose(c.p_sigma.numpy(), gold[f"{tag}/p_sigma"][t], rtol=5e-5, atol=5e-6)
+        np.testing.assert_allclose(c.p_c.numpy(), gold[f"{tag}/p_c"][t], rtol=5e-5, atol=5e-6)
+
+
+def _variant_table():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("searcher_variants", os.path.join(os.path.dirname(__file__), "golden", "searcher_variants.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("tag", sorted(_variant_table().VARIANTS))
+def test_searcher_option_variants_match_reference(tag):
+    """One seeded reference trajectory per searcher option not covered by `reference_golden.npz`: SGD with momentum, radius_init,
+    stdev bounds, no max-change, ClipUp configuration, normalized / linear / raw ranking, scale_learning_rate=False, default
+    population sizes, Adam on SNES, CEM bounds and maximisation, XNES learning rates (gaussian.py:543-1405)."""
+    mod = _variant_table()
+    algo, d, sense, fn, kw, gens = mod.VARIANTS[tag]
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "searcher_variants_golden.npz"))
+    prob = Problem(sense, mod.objective(fn), initial_bounds=(-5.12, 5.12), solution_length=d, vectorized=True, seed=11, dtype=torch.float32)
+    s = {"PGPE": PGPE, "SNES": SNES, "CEM": CEM, "XNES": XNES}[algo](prob, **kw)
+    tol = dict(rtol=3e-4, atol=3e-5) if algo == "XNES" else dict(rtol=2e-5, atol=3e-6)
+    for t in range(gens):
+        s.step()
+        assert len(s.population) == int(gold[f"{tag}/popsize"])
+        np.testing.assert_allclose(s.population.evals[:, 0].numpy(), gold[f"{tag}/f"][t], rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(s.status["center"].numpy(), gold[f"{tag}/mu"][t], **tol)
+        np.testing.assert_allclose(s.status["stdev"].numpy(), gold[f"{tag}/sigma"][t], **tol)
