@@ -26,12 +26,12 @@ out = {}
 for tag, (algo, D, sense, fn, kw, gens) in VARIANTS.items():
     prob = Problem(sense, objective(fn), initial_bounds=(-5.12, 5.12), solution_length=D, vectorized=True, seed=11, dtype=torch.float32)
     s = ALGOS[algo](prob, **kw)
-    mus, sigs, fs = [], [], []
+    mus, sigs, fs, xs = [], [], [], []
     for _ in range(gens):
         s.step()
         mus.append(s.status["center"].numpy().copy()); sigs.append(s.status["stdev"].numpy().copy())
-        fs.append(s.population.evals[:, 0].numpy().copy())
-    out[f"{tag}/mu"], out[f"{tag}/sigma"], out[f"{tag}/f"] = np.stack(mus), np.stack(sigs), np.stack(fs)
+        fs.append(s.population.evals[:, 0].numpy().copy()); xs.append(s.population.values.numpy().copy())
+    out[f"{tag}/mu"], out[f"{tag}/sigma"], out[f"{tag}/f"], out[f"{tag}/X"] = np.stack(mus), np.stack(sigs), np.stack(fs), np.stack(xs)
     out[f"{tag}/popsize"] = np.array(len(s.population))
 np.savez_compressed(os.path.join(HERE, "searcher_variants_golden.npz"), **out)
 print("wrote", len(out), "arrays", file=sys.stderr)

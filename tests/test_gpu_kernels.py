@@ -1,6 +1,7 @@
 """Parity of the sm_100a kernels (called through the C ABI of libevok.so via evotorch_b200.ops) against the numpy oracle
 and the golden vectors produced by the real reference.  Needs a CUDA device: run with `-m gpu` on the B200 box."""
 
+import os
 import math
 
 import numpy as np
@@ -871,3 +872,34 @@ def test_checkpoint_resume_is_bit_identical_on_gpu(tmp_path, mode):
     assert torch.equal(resumed.status["center"], straight.status["center"])
     assert torch.equal(resumed.status["stdev"], straight.status["stdev"])
     assert resumed.status["mean_eval"] == straight.status["mean_eval"]
+
+
+def _searcher_variants():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("searcher_variants", os.path.join(os.path.dirname(__file__), "golden", "searcher_variants.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("tag", sorted(t for t in _searcher_variants().VARIANTS if not t.startswith("xnes")))
+def test_searcher_option_variants_through_the_cuda_kernels(tag):
+    """The option variants of `tests/golden/searcher_variants.py` (SGD with momentum, stdev bounds, no max-change, ClipUp config,
+    normalized / linear / raw ranking, SNES without learning-rate scaling, Adam on SNES, CEM bounds / maximisation): the
+    reference's recorded populations go through the CUDA rank -> gradient -> update kernels generation by generation."""
+    mod = _searcher_variants()
+    algo, d, sense, fn, kw, gens = mod.VARIANTS[tag]
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "searcher_variants_golden.npz"))
+    mu, sg, X, f = (gold[f"{tag}/{k}"] for k in ("mu", "sigma", "X", "f"))
+    kw = {k: v for k, v in kw.items() if k not in ("stdev_init", "radius_init")}
+    prob = Problem(sense, mod.objective(fn), initial_bounds=(-5.12, 5.12), solution_length=d, device=DEV, seed=11, vectorized=True)
+    s = {"PGPE": PGPE, "SNES": SNES, "CEM": CEM}[algo](prob, center_init=C(mu[0]), stdev_init=C(sg[0]), **kw)
+    s.step()
+    assert len(s.population) == X.shape[1]
+    for t in range(gens - 1):
+        s._population.set_values(C(X[t]))
+        s._population.set_evals(C(f[t]))
+        s.step()
+        close(N(s.status["center"]), mu[t + 1], rtol=2e-5, atol=3e-6)
+        close(N(s.status["stdev"]), sg[t + 1], rtol=2e-5, atol=3e-6)
