@@ -110,7 +110,7 @@ class VecNE(Problem):
     def _get_env(self, num_envs: int):
         if not callable(self._env_source):
             return self._env_source  # a ready-made vectorised environment: its size is what it is
-        if self._env is None or self._env_size != num_envs:
+        if self._env is None or num_envs > self._env_size:  # a larger environment is reused: surplus sub-environments are padding (vecgymne.py:497)
             self._env, self._env_size = self._env_source(num_envs, **self._env_config), num_envs
         return self._env
 

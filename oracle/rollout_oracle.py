@@ -3,9 +3,11 @@
 `RunningNorm` net/runningnorm.py:229-533), written with the reference's own operation order: boolean-mask gather of the
 active observations, `update_and_normalize` on the gathered rows, scatter back into a clone, policy on the full batch.
 
-PARITY UNPINNED for the loop itself: the reference's VecGymNE needs `gymnasium`, which is not installed here, so this file
-could not be executed side by side with it (RunningNorm IS pinned: tests/golden/runningnorm_golden.npz comes from the real
-class).  The policy is the numpy MLP of es_oracle (pinned against the reference's `Policy`).
+PINNED: `tests/golden/rollout_golden.npz` holds scores, interaction / episode counters and observation statistics produced by the
+REAL `VecGymNE` loop (tests/golden/gen_rollout_golden.py runs it unmodified on the toy environment; gymnasium itself is absent,
+the functional stand-ins under tests/golden/_refstubs/gymnasium are enough for TorchWrapper / VecGymNE), and
+tests/test_rollout.py::test_rollout_oracle_matches_the_real_reference_rollouts checks this restatement against it.  RunningNorm is
+pinned separately (runningnorm_golden.npz), the policy is the numpy MLP of es_oracle (pinned against the reference's `Policy`).
 """
 
 from typing import Optional

@@ -1,14 +1,34 @@
+"""Minimal functional stand-ins for the gymnasium spaces the reference touches (test fixture only; gymnasium is absent)."""
+import numpy as np
+
+
 class Space:
-    pass
+    shape = None
+    dtype = None
 
 
 class Box(Space):
-    pass
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        if shape is None:
+            shape = np.asarray(low).shape
+        self.shape = tuple(shape)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+
+    def __repr__(self):
+        return f"Box({self.shape})"
 
 
 class Discrete(Space):
-    pass
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
 
 
 class MultiDiscrete(Space):
-    pass
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec)
+        self.shape = self.nvec.shape
+        self.dtype = np.dtype(np.int64)

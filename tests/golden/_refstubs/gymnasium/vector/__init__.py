@@ -1,5 +1,13 @@
 class VectorEnv:
-    pass
+    def __init__(self, *args, **kwargs):
+        pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        pass
 
 
 class SyncVectorEnv(VectorEnv):

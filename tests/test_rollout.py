@@ -167,3 +167,60 @@ def test_vecne_problem_drives_pgpe(device):
     torch.testing.assert_close(module(obs), want, rtol=1e-5, atol=1e-6)
     with pytest.raises(ValueError):
         VecNE(make_env, _net(n_in, 12, n_out), device=device).get_observation_stats()
+
+
+ROLLOUT_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "rollout_golden.npz"))
+ROLLOUT_VARIANTS = {
+    "plain": dict(),
+    "normalised": dict(observation_normalization=True),
+    "episodes_bonus": dict(observation_normalization=True, num_episodes=3, decrease_rewards_by=0.25, alive_bonus_schedule=(2, 5, 0.5)),
+    "bonus_single_step": dict(num_episodes=2, alive_bonus_schedule=(3, 0.3)),
+}
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("tag", list(ROLLOUT_VARIANTS))
+def test_vecne_matches_the_real_reference_rollouts(tag, device):
+    """`tests/golden/rollout_golden.npz` was produced by the reference's own `VecGymNE` loop (vecgymne.py:744-916) on the toy
+    environment: scores, interaction / episode counters and the running observation statistics must agree, including the second
+    call, where 41 solutions run in the 50 sub-environments left over from the first (9 padding environments)."""
+    from evotorch_b200 import SolutionBatch
+    from evotorch_b200.neuroevolution import VecNE
+
+    n_obs, n_hid, n_act = 12, 16, 4
+    prob = VecNE(lambda num_envs, **kw: ToyVecEnv(num_envs, n_obs, n_act, device=device, **kw), _net(n_obs, n_hid, n_act), env_config=dict(seed=3),
+                 device=device, **ROLLOUT_VARIANTS[tag])
+    for call, n in enumerate((50, 41)):
+        g = lambda key: ROLLOUT_GOLD[f"{tag}/{call}/{key}"]  # noqa: E731
+        batch = SolutionBatch(prob, popsize=n, empty=True)
+        batch.set_values(T(g("params"), device))
+        prob.evaluate(batch)
+        np.testing.assert_allclose(batch.evals[:, 0].cpu().numpy(), g("scores"), rtol=3e-4, atol=3e-4)
+        assert prob.interaction_count == int(g("interactions")) and prob.episode_count == int(g("episodes"))
+        assert prob.status["total_interaction_count"] == prob.interaction_count
+        if ROLLOUT_VARIANTS[tag].get("observation_normalization"):
+            stats = prob.get_observation_stats()
+            assert stats.count == int(g("stats_count"))
+            np.testing.assert_allclose(stats.sum.cpu().numpy(), g("stats_sum"), rtol=1e-4, atol=2e-3)
+            np.testing.assert_allclose(stats.sum_of_squares.cpu().numpy(), g("stats_sumsq"), rtol=1e-4, atol=2e-3)
+    assert prob._env_size == 50  # the larger environment was reused
+
+
+def test_rollout_oracle_matches_the_real_reference_rollouts():
+    """Pins oracle/rollout_oracle.py to the same golden file."""
+    n_obs, n_hid, n_act = 12, 16, 4
+    for tag, kw in ROLLOUT_VARIANTS.items():
+        okw = {k: v for k, v in kw.items() if k in ("num_episodes", "decrease_rewards_by")}
+        if "alive_bonus_schedule" in kw:
+            sched = kw["alive_bonus_schedule"]
+            okw["alive_bonus_schedule"] = sched if len(sched) == 3 else (sched[0], sched[0], sched[1])
+        norm = RO.RunningNormOracle(n_obs) if kw.get("observation_normalization") else None
+        total = 0
+        for call, n in enumerate((50, 41)):
+            env = ToyVecEnv(50, n_obs, n_act, seed=3).as_numpy()
+            scores, steps = RO.rollout(ROLLOUT_GOLD[f"{tag}/{call}/params"], n_obs, n_hid, n_act, "tanh", env, obs_norm=norm, **okw)
+            total += steps
+            np.testing.assert_allclose(scores, ROLLOUT_GOLD[f"{tag}/{call}/scores"], rtol=3e-4, atol=3e-4)
+            assert total == int(ROLLOUT_GOLD[f"{tag}/{call}/interactions"])
+            if norm is not None:
+                assert norm.count == int(ROLLOUT_GOLD[f"{tag}/{call}/stats_count"])
