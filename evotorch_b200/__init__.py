@@ -10,8 +10,8 @@ CMA-ES) as hand-written sm_100a CUDA kernels behind the reference's Problem / So
     searcher.run(100)
 """
 
-from . import algorithms, distributions, logging, objectives, optimizers, tools
+from . import algorithms, distributions, logging, neuroevolution, objectives, optimizers, testing, tools
 from .core import Problem, Solution, SolutionBatch
 
 __version__ = "0.1.0"
-__all__ = ["Problem", "Solution", "SolutionBatch", "algorithms", "distributions", "logging", "objectives", "optimizers", "tools"]
+__all__ = ["Problem", "Solution", "SolutionBatch", "algorithms", "distributions", "logging", "neuroevolution", "objectives", "optimizers", "testing", "tools"]

@@ -18,27 +18,10 @@ from typing import Any, Callable, Iterable, Optional, Union
 import torch
 
 from . import ops
+from .tools.hook import Hook
 from .tools.misc import ensure_tensor_length_and_dtype, extract_generator, make_gaussian, make_uniform, to_torch_dtype
 
 ObjectiveSense = Union[str, Iterable[str]]
-
-
-class Hook(list):
-    """A list of callables invoked together; dict results can be merged (tools/hook.py:25)."""
-
-    def __call__(self, *args, **kwargs):
-        result = None
-        for f in self:
-            result = f(*args, **kwargs)
-        return result
-
-    def accumulate_dict(self, *args, **kwargs) -> dict:
-        merged = {}
-        for f in self:
-            r = f(*args, **kwargs)
-            if r is not None:
-                merged.update(r)
-        return merged
 
 
 class Problem:
@@ -292,44 +275,62 @@ class Problem:
         dt, dev = self._tm(dtype, device, use_eval_dtype)
         return torch.as_tensor(data, dtype=dt, device=dev) if isinstance(data, torch.Tensor) else torch.tensor(data, dtype=dt, device=dev)
 
-    def make_empty(self, *size, num_solutions=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+    def _target(self, size, num_solutions, out, dtype, device, use_eval_dtype) -> torch.Tensor:
+        """The tensor a maker fills: `out` if given (then no size / dtype / device may be given), else a new one
+        (tools/tensormaker.py:60-140)."""
+        if out is not None:
+            if len(size) > 0 or num_solutions is not None or dtype is not None or device is not None or use_eval_dtype:
+                raise ValueError("When `out` is given, the arguments `size`, `num_solutions`, `dtype`, `device`, `use_eval_dtype` are not expected")
+            return out
         dt, dev = self._tm(dtype, device, use_eval_dtype)
         return torch.empty(self._size(size, num_solutions), dtype=dt, device=dev)
 
-    def make_zeros(self, *size, num_solutions=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
-        dt, dev = self._tm(dtype, device, use_eval_dtype)
-        return torch.zeros(self._size(size, num_solutions), dtype=dt, device=dev)
+    def make_empty(self, *size, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+        return self._target(size, num_solutions, out, dtype, device, use_eval_dtype)
 
-    def make_ones(self, *size, num_solutions=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
-        dt, dev = self._tm(dtype, device, use_eval_dtype)
-        return torch.ones(self._size(size, num_solutions), dtype=dt, device=dev)
+    def make_zeros(self, *size, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+        return self._target(size, num_solutions, out, dtype, device, use_eval_dtype).zero_()
 
-    def make_nan(self, *size, num_solutions=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
-        dt, dev = self._tm(dtype, device, use_eval_dtype)
-        return torch.full(self._size(size, num_solutions), float("nan"), dtype=dt, device=dev)
+    def make_ones(self, *size, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+        return self._target(size, num_solutions, out, dtype, device, use_eval_dtype).fill_(1)
 
-    def make_I(self, size: Optional[int] = None, *, dtype=None, device=None) -> torch.Tensor:
-        dt, dev = self._tm(dtype, device)
+    def make_nan(self, *size, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+        return self._target(size, num_solutions, out, dtype, device, use_eval_dtype).fill_(float("nan"))
+
+    def make_I(self, size=None, *, out=None, dtype=None, device=None, use_eval_dtype: bool = False) -> torch.Tensor:
+        """Identity matrix: n x n with n = `size` (an int or a 1-tuple), the solution length by default, or filled into `out`
+        (tools/tensormaker.py:427-508)."""
+        if isinstance(size, tuple):
+            if len(size) != 1:
+                raise ValueError(f"When the size argument is given as a tuple, the method `make_I(...)` expects the tuple to have only one"
+                                 f" element. The given tuple is {size}.")
+            size = size[0]
+        if out is not None:
+            if size is not None or dtype is not None or device is not None or use_eval_dtype:
+                raise ValueError("When `out` is given, the arguments `size`, `dtype`, `device`, `use_eval_dtype` are not expected")
+            if out.ndim != 2 or out.shape[0] != out.shape[1]:
+                raise ValueError(f"`out` was expected as a square matrix, but its shape is {tuple(out.shape)}")
+            out.zero_()
+            out.fill_diagonal_(1)
+            return out
+        dt, dev = self._tm(dtype, device, use_eval_dtype)
         return torch.eye(self._solution_length if size is None else int(size), dtype=dt, device=dev)
 
     def make_gaussian(self, *size, num_solutions=None, center=None, stdev=None, symmetric: bool = False, out=None, dtype=None,
-                      device=None, generator=None) -> torch.Tensor:
-        if out is None:
-            out = self.make_empty(*size, num_solutions=num_solutions, dtype=dtype, device=device)
+                      device=None, use_eval_dtype: bool = False, generator=None) -> torch.Tensor:
+        out = self._target(size, num_solutions, out, dtype, device, use_eval_dtype)
         return make_gaussian(out=out, center=center, stdev=stdev, symmetric=symmetric,
                              generator=self._generator if generator is None else generator)
 
-    def make_uniform(self, *size, num_solutions=None, lb=None, ub=None, out=None, dtype=None, device=None, generator=None) -> torch.Tensor:
-        if out is None:
-            out = self.make_empty(*size, num_solutions=num_solutions, dtype=dtype, device=device)
+    def make_uniform(self, *size, num_solutions=None, lb=None, ub=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False,
+                     generator=None) -> torch.Tensor:
+        out = self._target(size, num_solutions, out, dtype, device, use_eval_dtype)
         return make_uniform(out=out, lb=lb, ub=ub, generator=self._generator if generator is None else generator)
 
     def make_randint(self, *size, n, num_solutions=None, out=None, dtype=None, device=None, use_eval_dtype: bool = False,
                      generator=None) -> torch.Tensor:
         """Uniform random integers in [0, n-1], as integers or as floats (tools/tensormaker.py:681-749)."""
-        if out is None:
-            dt, dev = self._tm(dtype, device, use_eval_dtype)
-            out = torch.empty(self._size(size, num_solutions), dtype=dt, device=dev)
+        out = self._target(size, num_solutions, out, dtype, device, use_eval_dtype)
         gen = extract_generator(self._generator if generator is None else generator)
         n = int(n)
         if out.dtype.is_floating_point:
@@ -337,6 +338,12 @@ class Problem:
         else:
             out.random_(0, n, generator=gen)
         return out
+
+    def make_uniform_shaped_like(self, t: torch.Tensor, *, lb=None, ub=None) -> torch.Tensor:
+        return self.make_uniform(out=torch.empty_like(t), lb=lb, ub=ub)
+
+    def make_gaussian_shaped_like(self, t: torch.Tensor, *, center=None, stdev=None) -> torch.Tensor:
+        return self.make_gaussian(out=torch.empty_like(t), center=center, stdev=stdev)
 
     def ensure_tensor_length_and_dtype(self, t: Any, *, allow_scalar: bool = False, about: Optional[str] = None) -> torch.Tensor:
         return ensure_tensor_length_and_dtype(t, self._solution_length, self._dtype, about=about, allow_scalar=allow_scalar,
@@ -818,6 +825,12 @@ class SolutionBatch:
         out._evdata[:] = self._evdata
         return out
 
+    def __copy__(self) -> "SolutionBatch":  # copy.copy / copy.deepcopy give independent storage, like the reference (core.py:4391-4399)
+        return self.clone()
+
+    def __deepcopy__(self, memo) -> "SolutionBatch":
+        return self.clone()
+
     def __repr__(self) -> str:
         return f"<SolutionBatch: {len(self)} x {self.solution_length}, {self.dtype}, {self.device}>"
 
@@ -993,6 +1006,12 @@ class Solution:
 
     def clone(self) -> "Solution":
         return Solution(self._batch.clone(), 0)
+
+    def __copy__(self) -> "Solution":
+        return self.clone()
+
+    def __deepcopy__(self, memo) -> "Solution":
+        return self.clone()
 
     def to(self, device) -> "Solution":
         return Solution(self._batch.to(device), 0)
