@@ -413,8 +413,39 @@ class Problem:
         else:
             raise TypeError(f"The method `evaluate(...)` expected a Solution or a SolutionBatch as its argument, got {type(x)!r}.")
         self._before_eval_hook(batch)
-        self._evaluate_batch(batch)
+        self._evaluate_all(batch)
         self._finish_evaluation(batch)
+
+    @property
+    def aux_device(self) -> torch.device:
+        """Where `@on_aux_device` fitness functions run: the first visible GPU for a host-resident problem (if there is a GPU),
+        else the problem's own device (core.py:1657-1692)."""
+        if self._device.type == "cpu":
+            return torch.device("cuda") if torch.cuda.is_available() else self._device
+        return self._device
+
+    def _device_of_fitness_function(self) -> Optional[torch.device]:
+        """The device requested by `@on_device` / `@on_cuda` / `@on_aux_device` (or a plain `.device` attribute) on the objective
+        function or on an overridden `_evaluate_batch` / `_evaluate`; None if there is no such request (core.py:2502-2530)."""
+        for fn in (self._objective_func, self._evaluate_batch, self._evaluate):
+            if fn is None:
+                continue
+            if getattr(fn, "__evotorch_on_aux_device__", False):
+                return self.aux_device
+            if hasattr(fn, "device"):
+                return torch.device(fn.device)
+        return None
+
+    def _evaluate_all(self, batch: "SolutionBatch"):
+        """Evaluate on the device the fitness function asks for: the batch is moved there, evaluated, and the results are
+        copied back (core.py:2573-2585)."""
+        wanted = self._device_of_fitness_function()
+        if wanted is None or torch.device(wanted) == batch.device:
+            self._evaluate_batch(batch)
+            return
+        moved = batch.to(wanted)
+        self._evaluate_batch(moved)
+        batch._evdata[:] = moved._evdata.to(batch.device)
 
     def _finish_evaluation(self, batch: "SolutionBatch"):
         self._after_eval_status = {}

@@ -466,3 +466,50 @@ def test_searcher_option_variants_match_reference(tag):
         np.testing.assert_allclose(s.population.evals[:, 0].numpy(), gold[f"{tag}/f"][t], rtol=2e-5, atol=2e-4)
         np.testing.assert_allclose(s.status["center"].numpy(), gold[f"{tag}/mu"][t], **tol)
         np.testing.assert_allclose(s.status["stdev"].numpy(), gold[f"{tag}/sigma"][t], **tol)
+
+
+def test_decorators_and_device_aware_evaluation():
+    """decorators.py:170-960: vectorized / rowwise / expects_ndim / on_device / on_cuda / on_aux_device markers and how `Problem`
+    honours them (core.py:2502-2585).  (The reference's own tests/test_decorators.py, test_expects_ndim.py and test_func_alg.py pass
+    against this package through scripts/run_reference_tests.py.)"""
+    from evotorch_b200.decorators import expects_ndim, on_aux_device, on_cuda, on_device, pass_info, rowwise, vectorized
+
+    @rowwise
+    def norm2(x):
+        return torch.sum(x**2)
+
+    assert norm2(torch.ones(4)).shape == () and norm2(torch.ones(3, 4)).shape == (3,) and norm2(torch.ones(2, 3, 4)).shape == (2, 3)
+    prob = Problem("min", norm2, initial_bounds=(-1, 1), solution_length=4, seed=1)  # marked vectorized by @rowwise
+    batch = SolutionBatch(prob, popsize=6)
+    prob.evaluate(batch)
+    torch.testing.assert_close(batch.evals[:, 0], (batch.values**2).sum(-1))
+
+    @expects_ndim(2, 1, None)
+    def affine(a, b, tag):
+        assert tag == "x" and a.ndim == 2 and b.ndim == 1
+        return a @ b
+
+    assert affine(torch.ones(4, 3), torch.ones(3), "x").shape == (4,)
+    assert affine(torch.ones(5, 7, 4, 3), torch.ones(7, 3), "x").shape == (5, 7, 4)  # batch dims align on the right
+    assert affine(np.ones((4, 3), dtype=np.float32), torch.ones(3), "x").shape == (4,)
+    with pytest.raises(ValueError):
+        affine(torch.ones(3), torch.ones(3), "x")
+    assert expects_ndim(lambda v, s: v * s, (1, 0))(torch.ones(2, 3), 2.0).shape == (2, 3)  # scalars become tensors
+
+    assert vectorized(lambda x: x).__evotorch_vectorized__ and vectorized()(lambda x: x).__evotorch_vectorized__
+    assert pass_info(lambda **k: None).__evotorch_pass_info__ and on_aux_device(lambda x: x).__evotorch_on_aux_device__
+    assert on_cuda(lambda x: x).device == torch.device("cuda") and on_cuda(1)(lambda x: x).device == torch.device("cuda:1")
+
+    seen = []
+
+    @on_device("cpu")
+    @vectorized
+    def f(x):
+        seen.append(x.device)
+        return x.sum(-1)
+
+    p2 = Problem("min", f, initial_bounds=(-1, 1), solution_length=3, seed=1)
+    assert p2._device_of_fitness_function() == torch.device("cpu") and p2.aux_device.type in ("cpu", "cuda")
+    b2 = SolutionBatch(p2, popsize=4)
+    p2.evaluate(b2)
+    assert seen == [torch.device("cpu")] and not torch.isnan(b2.evals).any()
