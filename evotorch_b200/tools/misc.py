@@ -353,3 +353,35 @@ def empty_tensor_like(source, *, shape=None, length: Optional[int] = None, dtype
         shape = (int(shape),)
     return torch.empty(tuple(shape), dtype=source.dtype if dtype is None else to_torch_dtype(dtype),
                        device=source.device if device is None else device)
+
+
+def clone(x: Any, *, memo: Optional[dict] = None) -> Any:
+    """An independent copy of `x`: tensors and arrays are cloned (detached), containers are rebuilt around cloned items,
+    objects that know how to `clone()` themselves do so, anything else is deep-copied (tools/misc.py:588, tools/cloning.py:25)."""
+    import copy
+
+    memo = {} if memo is None else memo
+    key = id(x)
+    if key in memo:
+        return memo[key]
+    if isinstance(x, torch.nn.Module):
+        out = copy.deepcopy(x)
+    elif isinstance(x, torch.Tensor):
+        out = x.detach().clone()
+    elif isinstance(x, np.ndarray):
+        out = x.copy()
+    elif isinstance(x, (str, bytes, int, float, bool, type(None))):
+        out = x
+    elif isinstance(x, dict):
+        out = type(x)((clone(k, memo=memo), clone(v, memo=memo)) for k, v in x.items())
+    elif isinstance(x, (list, set, frozenset)):
+        out = type(x)(clone(v, memo=memo) for v in x)
+    elif isinstance(x, tuple):
+        items = [clone(v, memo=memo) for v in x]
+        out = type(x)(*items) if hasattr(x, "_fields") else tuple(items)
+    elif hasattr(x, "clone") and callable(x.clone):
+        out = x.clone()
+    else:
+        out = copy.deepcopy(x)
+    memo[key] = out
+    return out
