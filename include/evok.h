@@ -98,6 +98,8 @@ int evok_eval(int objective, const float* X, int64_t ldx, int64_t n_rows, int64_
  * identical to torch.argsort(f, descending=!higher_is_better, stable=True).
  * w: utilities (same length).  perm (nullable): the sorted order, worst first, as int64 (what
  * `argsort` returns).  ws: workspace of at least evok_rank_workspace_bytes(N) bytes.
+ * Implementation: N <= 8192 -> ONE launch (rank by counting, utilities / flags / permutation written by the same kernel);
+ * larger N -> stable LSD radix sort (4 passes x 8 bits) + a scatter kernel.  Both produce bit-identical results.
  * --------------------------------------------------------------------------------------------- */
 size_t evok_rank_workspace_bytes(int64_t N);
 int evok_rank(int method, const float* f, int64_t N, int higher_is_better, float* w, int64_t* perm, void* ws,
