@@ -18,13 +18,15 @@ from typing import Any, Callable, Iterable, Optional, Union
 import torch
 
 from . import ops
+from .tools.cloning import Clonable
 from .tools.hook import Hook
+from .tools.readonlytensor import as_read_only_tensor
 from .tools.misc import ensure_tensor_length_and_dtype, extract_generator, make_gaussian, make_uniform, to_torch_dtype
 
 ObjectiveSense = Union[str, Iterable[str]]
 
 
-class Problem:
+class Problem(Clonable):
     """Definition of an optimisation problem (core.py:365).  `objective_func` receives either one solution (1-D tensor)
     or, with `vectorized=True` / an `@vectorized`-marked function, the whole N x D population.  Built-in objectives from
     `evotorch_b200.objectives` additionally carry an `evok_objective_id`, which lets the searchers fuse evaluation into the
@@ -706,13 +708,14 @@ class SolutionBatch:
 
     @property
     def values(self) -> torch.Tensor:
-        """The N x D decision values (shares storage with what the kernels wrote; treat as read-only)."""
-        return self._data
+        """The N x D decision values as a ReadOnlyTensor sharing storage with what the kernels wrote (core.py:4135-4164);
+        `access_values()` gives the mutable tensor."""
+        return as_read_only_tensor(self._data)
 
     @property
     def evals(self) -> torch.Tensor:
-        """The N x (objectives + eval data) evaluation results (treat as read-only)."""
-        return self._evdata
+        """The N x (objectives + eval data) evaluation results as a ReadOnlyTensor (core.py:4101-4125)."""
+        return as_read_only_tensor(self._evdata)
 
     def access_values(self, *, keep_evals: bool = False) -> torch.Tensor:
         """Mutable view of the decision values; evaluations are forgotten (NaN) unless `keep_evals` (core.py:4166-4195)."""
@@ -970,15 +973,15 @@ class Solution:
 
     @property
     def values(self) -> torch.Tensor:
-        return self._batch._data[0]
+        return as_read_only_tensor(self._batch._data[0])
 
     @property
     def evals(self) -> torch.Tensor:
-        return self._batch._evdata[0]
+        return as_read_only_tensor(self._batch._evdata[0])
 
     @property
     def evaluation(self) -> torch.Tensor:
-        return self._batch._evdata[0]
+        return as_read_only_tensor(self._batch._evdata[0])
 
     def access_values(self, *, keep_evals: bool = False) -> torch.Tensor:
         return self._batch.access_values(keep_evals=keep_evals)[0]

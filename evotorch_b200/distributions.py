@@ -23,6 +23,8 @@ import torch
 
 from . import ops
 from .core import PhiloxRecipe
+from .tools.cloning import Clonable
+from .tools.readonlytensor import as_plain_tensor
 from .tools.misc import extract_generator, make_gaussian, to_torch_dtype
 from .tools.ranking import rank
 
@@ -34,7 +36,7 @@ def _philox_source(generator: Any):
                          and getattr(generator, "rng", "philox") == "philox") else None
 
 
-class Distribution:
+class Distribution(Clonable):
     """Base class of all search distributions (distributions.py:40-410)."""
 
     MANDATORY_PARAMETERS: set = set()
@@ -133,7 +135,8 @@ class Distribution:
             raise ValueError(f'`objective_sense` was expected as "min" or as "max". However, it was encountered as {objective_sense!r}.')
         if ranking_method is None:
             ranking_method = "raw"
-        fitnesses = torch.as_tensor(fitnesses, dtype=self.dtype)
+        fitnesses = as_plain_tensor(torch.as_tensor(fitnesses, dtype=self.dtype))  # e.g. `batch.evals[:, 0]` is a ReadOnlyTensor
+        samples = as_plain_tensor(samples)
         [num_samples, _] = samples.shape
         [num_fitnesses] = fitnesses.shape
         if num_samples != num_fitnesses:

@@ -13,6 +13,7 @@ from typing import Optional
 import torch
 
 from . import _native as nat
+from .tools.readonlytensor import as_plain_tensor
 
 OBJ_NONE, OBJ_SPHERE, OBJ_RASTRIGIN, OBJ_ACKLEY = 0, 1, 2, 3
 OBJECTIVE_IDS = {"sphere": OBJ_SPHERE, "rastrigin": OBJ_RASTRIGIN, "ackley": OBJ_ACKLEY}
@@ -90,13 +91,13 @@ def _vec(t: torch.Tensor, name: str, n: Optional[int] = None) -> torch.Tensor:
         raise ValueError(f"{name}: expected a contiguous 1-D float32 CUDA tensor, got {tuple(t.shape)} {t.dtype} {t.device}")
     if n is not None and t.numel() != n:
         raise ValueError(f"{name}: expected length {n}, got {t.numel()}")
-    return t
+    return as_plain_tensor(t)
 
 
 def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.float32 and t.ndim == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]):
         raise ValueError(f"{name}: expected a row-major 2-D float32 CUDA tensor, got {tuple(t.shape)} strides {t.stride()} {t.dtype}")
-    return t
+    return as_plain_tensor(t)
 
 
 # ------------------------------------------------------------------------------------------------ K1 / K2
@@ -226,7 +227,7 @@ def weights_adjust_(w: torch.Tensor, mode: int) -> torch.Tensor:
 
 
 def elite_mask(w: torch.Tensor, num_elites: int) -> torch.Tensor:
-    _vec(w, "weights")
+    w = _vec(w, "weights")
     n = w.numel()
     mask = torch.empty_like(w)
     ws = _rank_ws(w.device, n)

@@ -356,32 +356,7 @@ def empty_tensor_like(source, *, shape=None, length: Optional[int] = None, dtype
 
 
 def clone(x: Any, *, memo: Optional[dict] = None) -> Any:
-    """An independent copy of `x`: tensors and arrays are cloned (detached), containers are rebuilt around cloned items,
-    objects that know how to `clone()` themselves do so, anything else is deep-copied (tools/misc.py:588, tools/cloning.py:25)."""
-    import copy
+    """An independent copy of `x` (tools/misc.py:588): `deep_clone` with deep-copy as the fallback for unknown objects."""
+    from .cloning import deep_clone
 
-    memo = {} if memo is None else memo
-    key = id(x)
-    if key in memo:
-        return memo[key]
-    if isinstance(x, torch.nn.Module):
-        out = copy.deepcopy(x)
-    elif isinstance(x, torch.Tensor):
-        out = x.detach().clone()
-    elif isinstance(x, np.ndarray):
-        out = x.copy()
-    elif isinstance(x, (str, bytes, int, float, bool, type(None))):
-        out = x
-    elif isinstance(x, dict):
-        out = type(x)((clone(k, memo=memo), clone(v, memo=memo)) for k, v in x.items())
-    elif isinstance(x, (list, set, frozenset)):
-        out = type(x)(clone(v, memo=memo) for v in x)
-    elif isinstance(x, tuple):
-        items = [clone(v, memo=memo) for v in x]
-        out = type(x)(*items) if hasattr(x, "_fields") else tuple(items)
-    elif hasattr(x, "clone") and callable(x.clone):
-        out = x.clone()
-    else:
-        out = copy.deepcopy(x)
-    memo[key] = out
-    return out
+    return deep_clone(x, otherwise_deepcopy=True, memo={} if memo is None else memo)

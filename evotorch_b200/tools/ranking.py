@@ -14,6 +14,7 @@ from typing import Iterable
 import torch
 
 from .. import ops
+from .readonlytensor import as_plain_tensor
 
 
 def _sorted_positions(x: torch.Tensor, higher_is_better: bool) -> torch.Tensor:
@@ -23,6 +24,7 @@ def _sorted_positions(x: torch.Tensor, higher_is_better: bool) -> torch.Tensor:
 def centered(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.Tensor:
     """Linearly spaced utilities in [-0.5, 0.5]; the best solution gets +0.5 (tools/ranking.py:24-53)."""
     with torch.no_grad():
+        fitnesses = as_plain_tensor(fitnesses)
         x = fitnesses.reshape(-1)
         if ops.uses_kernels(x):
             return ops.rank(x.contiguous(), "centered", higher_is_better).reshape(fitnesses.shape)
@@ -37,6 +39,7 @@ def centered(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch
 def linear(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.Tensor:
     """Linearly spaced utilities in [0, 1] (tools/ranking.py:56-81)."""
     with torch.no_grad():
+        fitnesses = as_plain_tensor(fitnesses)
         x = fitnesses.reshape(-1)
         if ops.uses_kernels(x):
             return ops.rank(x.contiguous(), "linear", higher_is_better).reshape(fitnesses.shape)
@@ -51,6 +54,7 @@ def linear(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.T
 def nes(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.Tensor:
     """NES utilities max(0, ln(n/2+1) - ln(n-p)), normalised to sum 1, minus 1/n (tools/ranking.py:84-124)."""
     with torch.no_grad():
+        fitnesses = as_plain_tensor(fitnesses)
         x = fitnesses.reshape(-1)
         if ops.uses_kernels(x):
             return ops.rank(x.contiguous(), "nes", higher_is_better).reshape(fitnesses.shape)
@@ -70,6 +74,7 @@ def nes(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.Tens
 def normalized(fitnesses: torch.Tensor, *, higher_is_better: bool = True) -> torch.Tensor:
     """Standardised (zero mean, unit unbiased std) fitnesses, negated for minimisation (tools/ranking.py:127-160)."""
     with torch.no_grad():
+        fitnesses = as_plain_tensor(fitnesses)
         if ops.uses_kernels(fitnesses) and fitnesses.ndim == 1:
             return ops.rank(fitnesses.contiguous(), "normalized", higher_is_better)
         g = fitnesses if higher_is_better else -fitnesses
@@ -86,5 +91,5 @@ rankers = {"nes": nes, "centered": centered, "linear": linear, "normalized": nor
 
 def rank(fitnesses: Iterable[float], ranking_method: str, *, higher_is_better: bool) -> torch.Tensor:
     """Dispatch by name; KeyError on an unknown method exactly like the reference (tools/ranking.py:189-216)."""
-    fitnesses = torch.as_tensor(fitnesses)
+    fitnesses = as_plain_tensor(torch.as_tensor(fitnesses))
     return rankers[ranking_method](fitnesses, higher_is_better=higher_is_better)

@@ -513,3 +513,42 @@ def test_decorators_and_device_aware_evaluation():
     b2 = SolutionBatch(p2, popsize=4)
     p2.evaluate(b2)
     assert seen == [torch.device("cpu")] and not torch.isnan(b2.evals).any()
+
+
+def test_values_and_evals_are_read_only_tensors():
+    """core.py:4101-4164 + tools/readonlytensor.py: `.values` / `.evals` share storage with the population but refuse in-place
+    modification; library functions fed with them still return ordinary tensors."""
+    import copy
+
+    from evotorch_b200.tools import ReadOnlyTensor, as_read_only_tensor, storage_ptr
+
+    prob = Problem("min", sphere, initial_bounds=(-1, 1), solution_length=4, vectorized=True, seed=1)
+    batch = SolutionBatch(prob, popsize=6)
+    prob.evaluate(batch)
+    v, e = batch.values, batch.evals
+    assert isinstance(v, ReadOnlyTensor) and isinstance(e, ReadOnlyTensor) and isinstance(batch[0].values, ReadOnlyTensor)
+    assert storage_ptr(v) == storage_ptr(batch.access_values(keep_evals=True))  # a view, not a copy
+    with pytest.raises(TypeError):
+        v[0] = 1.0
+    with pytest.raises(TypeError):
+        v += 1
+    with pytest.raises(AttributeError):
+        v.zero_()
+    with pytest.raises(TypeError):
+        torch.add(v, 1, out=v)
+    with pytest.raises(ValueError):
+        v.numpy()[0, 0] = 3.0  # the numpy view is read-only too
+    assert type(v.clone()) is torch.Tensor and type(v[[0, 2]]) is torch.Tensor  # copies are ordinary tensors
+    assert isinstance(v[1:3], ReadOnlyTensor) and isinstance(v.reshape(-1), ReadOnlyTensor)  # views stay read-only
+    assert isinstance(copy.deepcopy(v), ReadOnlyTensor) and torch.equal(copy.deepcopy(v), v)
+    # reading works everywhere, and results of the library's own functions are writable tensors
+    w = rank(e[:, 0], "centered", higher_is_better=False)
+    assert type(w) is torch.Tensor
+    w += 1
+    dist = SymmetricSeparableGaussian({"mu": torch.zeros(4), "sigma": torch.ones(4)})
+    grads = dist.compute_gradients(v, e[:, 0], objective_sense="min", ranking_method="centered")
+    assert all(type(g) is torch.Tensor for g in grads.values())
+    batch.access_values()[:] = 0.5  # the sanctioned way to write
+    assert float(batch.values[0, 0]) == 0.5 and torch.isnan(batch.evals).all()
+    x = torch.arange(3.0)
+    assert storage_ptr(as_read_only_tensor(x)) == storage_ptr(x)
