@@ -2,7 +2,9 @@
 
 from ..policy import Policy, count_parameters, fill_parameters, parameter_vector
 from ..runningnorm import CollectedStats, ObsNormLayer, RunningNorm
-from . import runningnorm, vecrl
+from . import multilayered, parser, runningnorm, vecrl
+from .multilayered import MultiLayered
+from .parser import NetParsingError, str_to_net
 
 __all__ = ["Policy", "count_parameters", "fill_parameters", "parameter_vector", "RunningNorm", "ObsNormLayer", "CollectedStats", "runningnorm",
-           "vecrl"]
+           "vecrl", "multilayered", "parser", "MultiLayered", "NetParsingError", "str_to_net"]

@@ -46,9 +46,11 @@ def fill_parameters(net: nn.Module, vector: torch.Tensor):
 
 def _feedforward_spec(net: nn.Module) -> Optional[tuple]:
     """(layer widths, activations) if `net` is a Sequential of Linear(+bias) layers with supported activations, else None."""
+    from .net.multilayered import MultiLayered  # what str_to_net("A >> B >> C") builds
+
     if isinstance(net, nn.Linear):
         layers = [net]
-    elif isinstance(net, nn.Sequential):
+    elif isinstance(net, (nn.Sequential, MultiLayered)):
         layers = list(net)
     else:
         return None

@@ -24,13 +24,19 @@ class VecNE(Problem):
                  max_num_envs: Optional[int] = None, network_args: Optional[Mapping] = None, observation_normalization: bool = False,
                  decrease_rewards_by: Optional[float] = None, alive_bonus_schedule: Optional[tuple] = None,
                  action_noise_stdev: Optional[float] = None, num_episodes: int = 1, device=None, seed: Optional[int] = None):
+        self._env_source, self._env_config = env, dict(env_config or {})
         if isinstance(network, nn.Module):
             if network_args:
                 raise ValueError("`network_args` is expected as None when the network is given as a torch.nn.Module instance")
             net = network
+        elif isinstance(network, str):
+            # a structure string (net/parser.py): obs_length / act_length / obs_shape come from a one-environment probe, like the
+            # reference's `_env_constants_for_str_net` (vecgymne.py:68-80)
+            from .net.parser import str_to_net
+
+            net = str_to_net(network, **dict(self._probe_env_constants(), **dict(network_args or {})))
         else:
             net = network(**dict(network_args or {}))
-        self._env_source, self._env_config = env, dict(env_config or {})
         self._env, self._env_size = None, None
         self._max_num_envs = None if max_num_envs is None else int(max_num_envs)
         self._policy = Policy(net)
@@ -54,6 +60,22 @@ class VecNE(Problem):
         self._episode_count = 0
         super().__init__("max", initial_bounds=(-0.00001, 0.00001), solution_length=self._policy.parameter_length, device=device,
                          dtype=torch.float32, seed=seed)
+
+    def _probe_env_constants(self) -> dict:
+        env = self._env_source(1, **self._env_config) if callable(self._env_source) else self._env_source
+        obs = env.reset()
+        obs_shape = tuple(obs.shape[1:])
+        act_length = None
+        space = getattr(env, "single_action_space", None)
+        if space is not None and getattr(space, "shape", None):
+            act_length = int(space.shape[0])
+        for name in ("act_length", "action_length", "n_act"):
+            if act_length is None and hasattr(env, name):
+                act_length = int(getattr(env, name))
+        constants = {"obs_length": int(obs_shape[0]), "obs_shape": obs_shape}
+        if act_length is not None:
+            constants.update(act_length=act_length, act_shape=(act_length,))
+        return constants
 
     # ------------------------------------------------------------------ bookkeeping (vecgymne.py:457-494)
     @property

@@ -224,3 +224,26 @@ def test_rollout_oracle_matches_the_real_reference_rollouts():
             assert total == int(ROLLOUT_GOLD[f"{tag}/{call}/interactions"])
             if norm is not None:
                 assert norm.count == int(ROLLOUT_GOLD[f"{tag}/{call}/stats_count"])
+
+
+def test_network_structure_strings():
+    """net/parser.py: `str_to_net` (BASELINE config 4 writes its policy as "Linear(376, 256) >> Tanh() >> Linear(256, 17)"), the
+    `MultiLayered` it builds, and a VecNE problem whose network is such a string with obs_length / act_length filled in from the
+    environment.  (The reference's own tests/test_neuroevolution_net_parser.py passes against this parser.)"""
+    from evotorch_b200.neuroevolution import VecNE
+    from evotorch_b200.neuroevolution.net import MultiLayered, NetParsingError, str_to_net
+
+    net = str_to_net("Linear(376, 256) >> Tanh() >> Linear(256, 17)")
+    assert isinstance(net, MultiLayered) and len(net) == 3 and net[0].in_features == 376 and isinstance(net[1], nn.Tanh)
+    policy = Policy(net)
+    assert policy.parameter_length == 100_881 and policy._spec == ([376, 256, 17], ["tanh", "none"])  # the kernel path recognises it
+    x = torch.randn(5, 376)
+    ref = nn.Sequential(*list(net))
+    torch.testing.assert_close(net(x), ref(x))
+    with pytest.raises(NetParsingError, match="Unrecognized module class"):
+        str_to_net("Nope(3)")
+    with pytest.raises(NetParsingError, match=r"at line\(1\) at column\(8\): Unknown constant: n"):
+        str_to_net("Linear(n, 2)")
+    prob = VecNE(lambda num_envs, **kw: ToyVecEnv(num_envs, 10, 3, **kw), "Linear(obs_length, hidden) >> Tanh() >> Linear(hidden, act_length)",
+                 network_args=dict(hidden=7), env_config=dict(seed=1))
+    assert prob.solution_length == 10 * 7 + 7 + 7 * 3 + 3

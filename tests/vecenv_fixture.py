@@ -10,6 +10,7 @@ import torch
 class ToyVecEnv:
     def __init__(self, num_envs: int, n_obs: int, n_act: int, *, seed: int = 0, device="cpu", max_len: int = 9):
         g = np.random.default_rng(seed)
+        self.act_length = n_act
         self.A = torch.as_tensor(g.standard_normal((n_obs, n_obs)) * 0.4 / np.sqrt(n_obs), dtype=torch.float32, device=device)
         self.B = torch.as_tensor(g.standard_normal((n_obs, n_act)) * 0.5, dtype=torch.float32, device=device)
         self.c = torch.as_tensor(g.standard_normal(n_obs) * 0.8, dtype=torch.float32, device=device)
