@@ -112,10 +112,37 @@ _workspaces: dict = {}
 
 
 def workspace(device: torch.device, nbytes: int, tag: str = "ws") -> torch.Tensor:
-    """A per-(device, tag) scratch buffer that only grows, so pointers stay stable across generations."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """A per-(device, stream, tag) scratch buffer that only grows, so pointers stay stable across generations.
+    Keyed by the current stream: two searchers stepping on different streams never share scratch memory (a superseded
+    buffer goes back to the caching allocator, which is stream-ordered, so kernels already enqueued on this stream stay
+    valid).  A captured CUDA graph bakes the raw pointer in: captures run under `private_workspaces()` and own theirs."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, tag) if _private_depth == 0 else (dev, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+_private_depth = 0
+
+
+class private_workspaces:
+    """`with private_workspaces() as store:` -- every `workspace()` call inside allocates from (and is remembered in) a fresh
+    `store` instead of the shared table.  Wrapped around a CUDA-graph capture: the graph then writes only to scratch buffers
+    that it owns (keep `store` alive as long as the graph), so a later, larger request by anybody else -- which re-allocates
+    the shared buffer -- can never pull memory from under a graph that still replays into it."""
+
+    def __enter__(self) -> dict:
+        global _workspaces, _private_depth
+        self._saved = _workspaces
+        _workspaces = self.store = {}
+        _private_depth += 1
+        return self.store
+
+    def __exit__(self, *exc):
+        global _workspaces, _private_depth
+        _workspaces = self._saved
+        _private_depth -= 1
+        return False

@@ -105,6 +105,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         """Everything but the captured CUDA graph (re-captured on the first step after loading)."""
         state = dict(self.__dict__)
         state["_graph"] = None
+        state.pop("_graph_workspaces", None)
         return state
 
     # ------------------------------------------------------------------ generations
@@ -132,7 +133,8 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         dist, prob = self._distribution, self.problem
         ok = (isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
               and prob.evok_objective_id is not None and len(prob.senses) == 1 and prob.eval_data_length == 0
-              and (self._optimizer is None or isinstance(self._optimizer, ClipUp)))
+              and (self._optimizer is None or isinstance(self._optimizer, ClipUp))
+              and len(prob.before_eval_hook) == 0)  # a Python hook between sampling and evaluation cannot be replayed
         if self._distributed:  # the sharded generation has no Python between its kernels / collectives either
             return (ok and not prob.stores_solution_stats and len(prob.before_eval_hook) == 0 and len(prob.after_eval_hook) == 0
                     and len(prob.before_grad_hook) == 0 and len(prob.after_grad_hook) == 0)  # Python hooks do not replay
@@ -179,8 +181,11 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         self._graph_base_stream = prob._philox_stream
         graph = torch.cuda.CUDAGraph()
         before = ops.launch_count()
-        with torch.cuda.graph(graph):
+        from .. import _native as nat
+
+        with nat.private_workspaces() as store, torch.cuda.graph(graph):  # the graph owns the scratch buffers it writes to
             self._graph_body(self._graph_base_stream, self._graph_counter)
+        self._graph_workspaces = store
         self._graph_kernels = ops.launch_count() - before  # kernels of libevok.so inside one replay
         ops.count_replayed_launches(-self._graph_kernels)  # the capture itself executed nothing
         self._graph_counter.zero_()
@@ -193,7 +198,6 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             self._step_eager()
             self._capture_graph()
             return
-        prob._before_eval_hook(pop)
         self._graph.replay()
         ops.count_replayed_launches(self._graph_kernels)
         prob._philox_stream += 1  # keep the host-side stream counter in step with the device-side one
@@ -230,12 +234,29 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             self._update_distribution(fetched[0]["gradients"])
         self._mean_eval = fetched[0]["mean_eval"]
 
+    def _sync_initial_state(self):
+        """First sharded generation: every rank adopts rank 0's distribution and optimizer state (replicated-update invariant;
+        with center_init=None / seed=None the ranks would otherwise start from different centres and keep a constant offset)."""
+        from ..distributed import broadcast_search_state
+
+        dist_ = self._distribution
+        tensors = [v for v in dist_.parameters.values() if isinstance(v, torch.Tensor)]
+        opt = self._optimizer
+        for name in ("_velocity", "_m", "_v", "_buf"):
+            t = getattr(opt, name, None) if opt is not None else None
+            if isinstance(t, torch.Tensor):
+                tensors.append(t)
+        broadcast_search_state(tensors)
+        self._state_synced = True
+
     def _step_distributed(self):
         """Every rank: sample/evaluate its shard, global ranking, all-reduced gradients, replicated update
         (replaces gaussian.py:199-272).  With `enable_cuda_graph()` the whole sequence, NCCL collectives included, is captured
         once and replayed.  NOTE: replayed collectives run on the replaying stream, eager ones on NCCL's internal stream; do not
         interleave a graph-mode searcher with other collectives on the same process group without a device synchronisation."""
         prob = self.problem
+        if not self.__dict__.get("_state_synced", False):
+            self._sync_initial_state()
         if os.environ.get("EVOTORCH_B200_PEER", "0") == "1" and getattr(prob, "_peer_exchange", None) is None and not self.__dict__.get("_peer_tried"):
             # opt-in by environment: fuse the two exchanges of the generation into the producing kernels (evotorch_b200/peer.py)
             self._peer_tried = True
@@ -259,9 +280,12 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = ops.launch_count()
-            with torch.cuda.graph(graph):
+            from .. import _native as nat
+
+            with nat.private_workspaces() as store, torch.cuda.graph(graph):
                 self._distributed_body(in_place=True)
                 prob.philox_stream_offset.add_(1)
+            self._graph_workspaces = store
             self._graph_kernels = ops.launch_count() - before
             ops.count_replayed_launches(-self._graph_kernels)
             prob._philox_stream = base  # the capture consumed one host-side stream id without running anything

@@ -530,11 +530,13 @@ class Problem(Clonable):
             n = len(batch)
             if distribution.SYMMETRIC and n % 2 != 0:
                 raise ValueError(f"Symmetric sampling cannot be done if the number of solutions is odd: {n}")
-            self._before_eval_hook(batch)
             seed, stream_id = self.next_philox_stream()
             mu, sigma = distribution.mu.contiguous(), distribution.sigma.contiguous()
             batch.recipe = PhiloxRecipe(seed=seed, stream_id=stream_id, row0=self.philox_row0, n_rows=n, solution_length=self._solution_length,
                                         symmetric=distribution.SYMMETRIC, stream_offset=self.philox_stream_offset, mu=mu, sigma=sigma)
+            # the hook runs AFTER the new population is defined (core.py:2559 of the reference calls it inside evaluate(), after
+            # distribution.sample): `batch.values` regenerates the new samples from the recipe.  A lazy batch is read-only.
+            self._before_eval_hook(batch)
             peer = getattr(self, "_active_peer", None)
             if peer is not None:  # sharded generation over NVLink peer memory: the fitness all-gather happens inside the kernel
                 ops.sample_eval_push(obj, None, mu, sigma, n_rows=n, symmetric=distribution.SYMMETRIC, seed=seed, stream_id=stream_id,
@@ -545,8 +547,11 @@ class Problem(Clonable):
             self._finish_evaluation(batch)
             return
         values = batch.access_values()
+        # before-eval hooks must see (and may edit) the freshly sampled values before they are evaluated (core.py:2559 of the
+        # reference: the hook is called inside evaluate(), after distribution.sample): with hooks registered the sampling and the
+        # evaluation stay two kernels with the hook in between
         fused = (obj is not None and self.rng == "philox" and ops.uses_kernels(values) and len(self._senses) == 1
-                 and hasattr(distribution, "SYMMETRIC") and ops.uses_kernels(distribution.mu))
+                 and hasattr(distribution, "SYMMETRIC") and ops.uses_kernels(distribution.mu) and len(self._before_eval_hook) == 0)
         if not fused:
             distribution.sample(out=values, generator=self)
             self.evaluate(batch)
@@ -554,7 +559,6 @@ class Problem(Clonable):
         n = values.shape[0]
         if distribution.SYMMETRIC and n % 2 != 0:
             raise ValueError(f"Symmetric sampling cannot be done if the leftmost dimension of the target tensor is odd: {tuple(values.shape)}")
-        self._before_eval_hook(batch)
         seed, stream_id = self.next_philox_stream()
         evdata = batch._evdata
         direct = evdata.shape[1] == 1 and evdata.dtype == torch.float32 and evdata.is_contiguous()

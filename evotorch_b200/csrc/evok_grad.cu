@@ -455,10 +455,9 @@ static int grad_impl(int form, const float* X, int64_t ldx, const float* w, cons
     cudaMemsetAsync(out_sigma, 0, (size_t)D * 4, st);
     return 0;
   }
-  static const int use_tma = [] {
-    const char* e = getenv("EVOK_GRAD_TMA");
-    return e ? atoi(e) : EVOK_GRAD_TMA_DEFAULT;
-  }();
+  // read per call (a getenv is ~100 ns): the parity tests run both implementations in one process
+  const char* tma_env = getenv("EVOK_GRAD_TMA");
+  const int use_tma = tma_env ? atoi(tma_env) : EVOK_GRAD_TMA_DEFAULT;
   if (use_tma && !regen && vec_ok && form != EVOK_GRAD_MOMENTS && D >= 512 && n_units >= 4096) {
     const int n_coltiles = (int)((D + kTmaCols - 1) / kTmaCols);
     int64_t chunks = (int64_t)kNumSMs * EVOK_GRAD_TMA_CTAS_PER_SM / n_coltiles;

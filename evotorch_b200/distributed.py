@@ -61,14 +61,37 @@ def all_gather_rows(local: torch.Tensor, counts: list) -> torch.Tensor:
 
 
 def broadcast_seed(problem) -> None:
-    """Make every rank draw from the same Philox key (rank 0's) -- required for the population to be rank-count invariant."""
+    """Make every rank draw from the same Philox key (rank 0's) -- required for the population to be rank-count invariant.
+    With `rng="torch"` (CPU problems, non-fp32 dtypes) the noise comes from each rank's own torch generator, whose stream
+    cannot be indexed by global row: the generators are then re-seeded with a per-rank offset of rank 0's seed, so that the
+    shards hold DIFFERENT samples (the same seed on every rank would make the global population `world_size` duplicated
+    blocks); the trajectory is then reproducible for a given world size, not across world sizes."""
     rank_, ws = world()
     if ws == 1 or getattr(problem, "_seed_synced", False):
         return
     t = torch.tensor([problem._philox_seed & 0x7FFFFFFFFFFFFFFF, problem._philox_stream], dtype=torch.int64, device=problem.device)
     dist.broadcast(t, src=0)
     problem._philox_seed, problem._philox_stream = int(t[0].item()), int(t[1].item())
+    if problem.rng == "torch":
+        problem.generator.manual_seed((problem._philox_seed + 0x9E3779B97F4A7C15 * (rank_ + 1)) & 0x7FFFFFFFFFFFFFFF)
     problem._seed_synced = True
+
+
+def broadcast_search_state(tensors: list) -> None:
+    """Replicated-update invariant: every rank must start from rank 0's distribution and optimizer state.  With
+    `center_init=None` each rank draws its own centre (and with `seed=None` its own seed), so the searchers call this once
+    before their first sharded generation (in place, src = rank 0)."""
+    rank_, ws = world()
+    if ws == 1:
+        return
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.numel() > 0:
+            if t.is_contiguous():
+                dist.broadcast(t, src=0)
+            else:
+                c = t.contiguous()
+                dist.broadcast(c, src=0)
+                t.copy_(c)
 
 
 def _usable_peer_exchange(problem, dev_dist, popsize: int, ws: int):
@@ -80,10 +103,10 @@ def _usable_peer_exchange(problem, dev_dist, popsize: int, ws: int):
 
     ok = (peer.popsize == popsize and peer.world == ws and problem.evok_objective_id is not None and problem.rng == "philox"
           and len(problem.senses) == 1 and problem.eval_data_length == 0 and hasattr(dev_dist, "partial_gradients")
-          and hasattr(dev_dist, "SYMMETRIC") and ops.uses_kernels(dev_dist.mu))
+          and hasattr(dev_dist, "SYMMETRIC") and ops.uses_kernels(dev_dist.mu) and len(problem.before_eval_hook) == 0)
     if not ok:
         raise ValueError("the attached PeerExchange does not fit this generation (needs: same popsize and world size, a built-in "
-                         "objective, rng='philox', one objective, a separable Gaussian on CUDA float32)")
+                         "objective, rng='philox', one objective, a separable Gaussian on CUDA float32, no before_eval_hook)")
     return peer
 
 

@@ -74,6 +74,16 @@ def _worker(rank, world, init_file, out_dir):
                 s.step()
                 traj.append(torch.cat([s.status["center"], s.status["stdev"], torch.tensor([s.status["mean_eval"]])]))
             torch.save(torch.stack(traj), os.path.join(out_dir, f"{kind}_{rank}.pt"))
+        # unseeded problem, no centre given, torch RNG: every rank would start from its own centre and (with equal seeds) draw the
+        # same noise -- the searcher must adopt rank 0's state and the ranks must sample different shards
+        for seed in (None, 5):
+            prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=6, vectorized=True, seed=seed)
+            s = PGPE(prob, popsize=20, center_learning_rate=0.4, stdev_learning_rate=0.1, stdev_init=1.0, distributed=True)
+            for _ in range(3):
+                s.step()
+            shard = next(iter(prob._grad_batches.values())).values.clone()
+            torch.save({"state": torch.cat([s.status["center"], s.status["stdev"], s._optimizer._velocity]), "shard": shard},
+                       os.path.join(out_dir, f"unseeded_{seed}_{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -110,3 +120,8 @@ def test_two_rank_generation_equals_single_process():
             r1 = torch.load(os.path.join(tmp, f"{kind}_1.pt")).numpy()
             np.testing.assert_array_equal(r0, r1)  # replicated update: every rank holds identical mu / sigma
             np.testing.assert_allclose(r0, ref, rtol=2e-5, atol=2e-6, err_msg=kind)
+        for seed in (None, 5):
+            a = torch.load(os.path.join(tmp, f"unseeded_{seed}_0.pt"))
+            b = torch.load(os.path.join(tmp, f"unseeded_{seed}_1.pt"))
+            assert torch.equal(a["state"], b["state"])  # one replicated distribution / optimizer state
+            assert not torch.equal(a["shard"], b["shard"])  # but different samples in the two shards
