@@ -42,8 +42,13 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         problem.ensure_numeric()
         problem.ensure_unbounded()
         SearchAlgorithm.__init__(self, problem, center=self._get_mu, stdev=self._get_sigma, mean_eval=self._get_mean_eval)
-        if num_interactions is not None or popsize_max is not None:
-            raise NotImplementedError("adaptive population size (num_interactions / popsize_max) is an RL-only feature and out of scope")
+        # adaptive population size (gaussian.py:114-130, :299-349 of the reference): keep sampling `popsize`-sized populations until
+        # the problem has reported more than `num_interactions` simulator interactions (or `popsize_max` solutions)
+        self._num_interactions = None if num_interactions is None else int(num_interactions)
+        if popsize_max is not None and num_interactions is None:
+            raise ValueError("`popsize_max` was expected as None, because `num_interactions` is None."
+                             " The argument `popsize_max` is meaningful only when `num_interactions` is given.")
+        self._popsize_max = None if popsize_max is None else int(popsize_max)
         self._ensure_even_popsize = bool(ensure_even_popsize)
         if self._ensure_even_popsize and (int(popsize) % 2) != 0 and not distributed:
             raise ValueError(f"`popsize` was expected as an even number. However, the received `popsize` is {popsize}.")
@@ -110,12 +115,34 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
 
     # ------------------------------------------------------------------ generations
     def _fill_and_eval_pop(self):
+        if self._num_interactions is not None:
+            self._fill_and_eval_adaptive_pop()
+            return
         if self._population is None:
             if self.problem.lazy_population:
                 self._population = LazySolutionBatch(self.problem, self._popsize, device=self._distribution.device)
             else:
                 self._population = SolutionBatch(self.problem, popsize=self._popsize, device=self._distribution.device, empty=True)
         self.problem.sample_and_evaluate(self._distribution, self._population)
+
+    def _fill_and_eval_adaptive_pop(self):
+        """gaussian.py:299-349: populations of `popsize` solutions are sampled and evaluated (each through the same fused K1+K2
+        path as a fixed-size population) until the interaction count reported by the problem (`status["total_interaction_count"]`)
+        has grown by more than `num_interactions`, or `popsize_max` solutions exist; the generation's population is their
+        concatenation.  The population size then varies between generations, so this mode is never graph-captured."""
+        prob = self.problem
+        first = prob.status.get("total_interaction_count", 0)
+        populations, total = [], 0
+        while True:
+            newpop = SolutionBatch(prob, popsize=self._popsize, device=self._distribution.device, empty=True)
+            total += len(newpop)
+            prob.sample_and_evaluate(self._distribution, newpop)
+            populations.append(newpop)
+            if self._popsize_max is not None and total >= self._popsize_max:
+                break
+            if prob.status["total_interaction_count"] - first > self._num_interactions:
+                break
+        self._population = populations[0] if len(populations) == 1 else SolutionBatch.cat(populations)
 
     # ------------------------------------------------------------------ CUDA-graph replay of a whole generation
     def enable_cuda_graph(self, enabled: bool = True):
@@ -131,7 +158,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         from ..optimizers import ClipUp
 
         dist, prob = self._distribution, self.problem
-        ok = (isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
+        ok = (self._num_interactions is None and isinstance(dist, SeparableGaussian) and ops.uses_kernels(dist.mu) and prob.rng == "philox"
               and prob.evok_objective_id is not None and len(prob.senses) == 1 and prob.eval_data_length == 0
               and (self._optimizer is None or isinstance(self._optimizer, ClipUp))
               and len(prob.before_eval_hook) == 0)  # a Python hook between sampling and evaluation cannot be replayed
@@ -226,6 +253,7 @@ class GaussianSearchAlgorithm(SearchAlgorithm, SinglePopulationAlgorithmMixin):
 
     def _distributed_body(self, in_place: bool):
         fetched = self.problem.sample_and_compute_gradients(self._distribution, self._popsize, obj_index=self._obj_index,
+                                                            num_interactions=self._num_interactions, popsize_max=self._popsize_max,
                                                             ranking_method=self._ranking_method,
                                                             ensure_even_popsize=self._ensure_even_popsize)
         if in_place:

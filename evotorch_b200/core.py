@@ -37,11 +37,18 @@ class Problem(Clonable):
                  seed: Optional[int] = None, num_actors=None, actor_config=None, num_gpus_per_actor=None, num_subbatches=None,
                  subbatch_size=None, store_solution_stats: Optional[bool] = None, vectorized: Optional[bool] = None,
                  rng: Optional[str] = None, lazy_population: bool = False):
-        if num_actors not in (None, 0):
-            raise NotImplementedError(
-                "Ray actors are not part of evotorch_b200: shard the population over GPUs with torch.distributed instead "
-                "(launch with torchrun and pass distributed=True to the searcher; see evotorch_b200.distributed)."
-            )
+        if num_actors not in (None, 0, 1):
+            # Drop-in behaviour for scripts written against the reference (e.g. its quick-start, tests/test_examples.py:29-78):
+            # the request is accepted and mapped onto what replaces Ray here -- the ranks of torch.distributed when the script was
+            # launched with torchrun (searchers built with distributed=True then shard the population over them), else this one
+            # process, which evaluates the whole population with the vectorised / fused kernels.
+            import warnings
+
+            warnings.warn(
+                f"num_actors={num_actors!r}: evotorch_b200 has no Ray actors. The population is evaluated by this process"
+                " (or sharded over the torch.distributed ranks when launched with torchrun and distributed=True is given to the"
+                " searcher; see evotorch_b200.distributed).", stacklevel=2)
+        self._requested_num_actors = num_actors
         self._dtype = torch.float32 if dtype is None else to_torch_dtype(dtype)
         if eval_dtype is None:
             self._eval_dtype = self._dtype if self._dtype.is_floating_point else torch.float32
@@ -588,9 +595,7 @@ class Problem(Clonable):
         When torch.distributed is initialised with more than one rank, every rank samples and evaluates its own row shard,
         fitnesses are all-gathered for a GLOBAL ranking and the partial gradients are all-reduced (see distributed.py); this
         replaces the reference's Ray actors, which rank locally per actor."""
-        if num_interactions is not None or popsize_max is not None:
-            raise NotImplementedError("adaptive population size (num_interactions / popsize_max) is an RL-only feature and out of scope")
-        from .distributed import sharded_sample_and_gradients
+        from .distributed import adaptive_sample_and_gradients, sharded_sample_and_gradients
 
         popsize = int(popsize)
         if ensure_even_popsize and popsize % 2 != 0:
@@ -599,10 +604,22 @@ class Problem(Clonable):
         hooks = self.__dict__
         if len(hooks.get("_before_grad_hook", ())) >= 1:
             hooks["_before_grad_hook"]()
-        result = sharded_sample_and_gradients(self, distribution, popsize, obj_index=obj_index, ranking_method=ranking_method)
+        if num_interactions is not None:  # adaptive population size (core.py:3239-3282)
+            result = adaptive_sample_and_gradients(self, distribution, popsize, num_interactions=int(num_interactions),
+                                                   popsize_max=None if popsize_max is None else int(popsize_max), obj_index=obj_index,
+                                                   ranking_method=ranking_method)
+        else:
+            result = sharded_sample_and_gradients(self, distribution, popsize, obj_index=obj_index, ranking_method=ranking_method)
         if len(hooks.get("_after_grad_hook", ())) >= 1:
             self._after_eval_status = hooks["_after_grad_hook"].accumulate_dict([result])
         return [result] if with_stats else result["gradients"]
+
+    def _get_local_interaction_count(self) -> int:
+        """Simulator interactions made so far by this process (core.py:2736-2747; RL problems override it).  The default reads
+        the `total_interaction_count` status item."""
+        if "total_interaction_count" in self._after_eval_status:
+            return int(self._after_eval_status["total_interaction_count"])
+        raise NotImplementedError
 
     def compare_solutions(self, a: "Solution", b: "Solution", obj_index: Optional[int] = None) -> float:
         i = self.normalize_obj_index(obj_index)

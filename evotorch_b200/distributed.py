@@ -176,3 +176,38 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
         grads = {k: v.to(home_device) for k, v in grads.items()}
         mean_eval = mean_eval.to(home_device)
     return {"gradients": grads, "num_solutions": popsize, "mean_eval": mean_eval}
+
+
+def adaptive_sample_and_gradients(problem, distribution, popsize: int, *, num_interactions: int, popsize_max: Optional[int], obj_index: int,
+                                  ranking_method: Optional[str]) -> dict:
+    """`_sample_and_compute_gradients` with an interaction-count threshold (core.py:3239-3282): batches of `popsize`
+    solutions are sampled and evaluated until this process has made more than `num_interactions` simulator interactions (or
+    holds `popsize_max` solutions); the gradients are computed over their concatenation (same kernels, K3 + K4, as the
+    fixed-size path).  The number of solutions then differs from rank to rank and from generation to generation, which the
+    global-ranking protocol of `sharded_sample_and_gradients` cannot shard: single-process only."""
+    from .core import SolutionBatch
+
+    if world()[1] > 1:
+        raise NotImplementedError("adaptive population size (num_interactions) is not available with a population sharded over ranks: "
+                                  "the global ranking needs a fixed, common population size")
+    home_device = distribution.device
+    dev_dist = distribution.to(problem.device)
+    first = problem._get_local_interaction_count()
+    batches, total = [], 0
+    while True:
+        batch = SolutionBatch(problem, popsize, device=problem.device, empty=True)
+        problem.sample_and_evaluate(dev_dist, batch)
+        batches.append(batch)
+        total += popsize
+        if problem._get_local_interaction_count() - first > num_interactions:
+            break
+        if popsize_max is not None and total >= popsize_max:
+            break
+    merged = batches[0] if len(batches) == 1 else SolutionBatch.cat(batches)
+    grads = dev_dist.compute_gradients(merged.access_values(keep_evals=True), merged.access_evals(obj_index),
+                                       objective_sense=problem.senses[obj_index], ranking_method=ranking_method)
+    mean_eval = torch.mean(merged.access_evals(obj_index))
+    if home_device != problem.device:
+        grads = {k: v.to(home_device) for k, v in grads.items()}
+        mean_eval = mean_eval.to(home_device)
+    return {"gradients": grads, "num_solutions": len(merged), "mean_eval": mean_eval}

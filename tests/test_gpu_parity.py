@@ -221,3 +221,75 @@ def _recorded_sampler(c, zt):
         return zt, ys, xs
 
     return sample
+
+
+# ------------------------------------------------------------------------------------------------ advisor regressions
+def test_sampler_writes_the_philox_known_answer():
+    """Seed 0, stream 0, direction 0, columns 0..3 is Random123's first known-answer vector (counter 0, key 0): the kernel
+    must write its Box-Muller image (oracle restatement pinned by tests/test_oracle_golden.py)."""
+    X = torch.empty(2, 4, device=DEV)
+    ops.sample_eval(ops.OBJ_NONE, X, torch.zeros(4, device=DEV), torch.ones(4, device=DEV), n_rows=2, symmetric=True, seed=0, stream_id=0)
+    x, y, z, w = 0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8
+
+    def bm(a, b):
+        u1 = a * 2.0**-32 + 2.0**-33
+        th = 2 * np.pi * (b * 2.0**-32 + 2.0**-33)
+        r = np.sqrt(-2 * np.log(u1))
+        return r * np.cos(th), r * np.sin(th)
+
+    expect = np.array([*bm(x, y), *bm(z, w)])
+    close(N(X[0]), expect, rtol=0, atol=2e-5)
+    close(N(X[1]), -expect, rtol=0, atol=2e-5)
+
+
+def test_before_eval_hook_sees_and_edits_the_fresh_population():
+    """core.py:2559 of the reference: the hook runs inside evaluate(), AFTER distribution.sample -- it must see the new
+    samples and its edits must be what gets evaluated (with hooks registered the sample and evaluate kernels are not fused)."""
+    D, n = 64, 256
+    prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=D, device=DEV, seed=4)
+    seen = []
+
+    def hook(batch):
+        v = batch.access_values(keep_evals=True)
+        seen.append(v.clone())
+        v.clamp_(-0.5, 0.5)
+
+    prob.before_eval_hook.append(hook)
+    s = PGPE(prob, popsize=n, center_learning_rate=0.3, stdev_learning_rate=0.1, stdev_init=1.0).enable_cuda_graph()
+    for g in range(4):
+        s.step()
+        X, f = s.population.values, s.population.evals[:, 0]
+        assert float(X.abs().max()) <= 0.5  # the edit survived
+        close(N(f), O.sphere(N(X)), rtol=1e-5)  # and is what was evaluated
+        assert len(seen) == g + 1 and float(seen[-1].abs().max()) > 0.5  # the hook saw the fresh, unclamped samples
+        if g > 0:
+            assert not torch.equal(seen[-1], seen[-2])
+    assert s._graph is None  # a Python hook cannot be replayed: the searcher stayed on the eager path
+
+
+def test_captured_graph_owns_its_workspaces():
+    """A CUDA graph bakes raw workspace pointers in.  A later, larger workspace request (here: ranking a bigger vector and a
+    second searcher) must not invalidate the memory a captured graph still writes to: the replayed trajectory stays
+    bit-identical to eager stepping."""
+    def make():
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=512, device=DEV, seed=9)
+        return PGPE(prob, popsize=20_000, center_learning_rate=0.4, stdev_learning_rate=0.1, stdev_init=1.0)
+
+    eager, graph = make(), make().enable_cuda_graph()
+    for _ in range(3):
+        eager.step(); graph.step()
+    assert graph._graph is not None
+    # bigger requests on every shared workspace tag, then garbage that would land in recycled memory
+    big = torch.randn(3_000_000, device=DEV)
+    ops.rank(big, "centered", False)
+    other = PGPE(Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=4096, device=DEV, seed=1), popsize=60_000,
+                 center_learning_rate=0.4, stdev_learning_rate=0.1, stdev_init=1.0)
+    other.run(3)
+    del big
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 22,), float("nan"), device=DEV) for _ in range(8)]
+    for _ in range(3):
+        eager.step(); graph.step(); other.step()
+        for j in junk:
+            j.fill_(float("nan"))
+    assert torch.equal(eager.status["center"], graph.status["center"]) and torch.equal(eager.status["stdev"], graph.status["stdev"])

@@ -202,8 +202,8 @@ def test_solution_batch_semantics():
     assert len(SolutionBatch.cat(pieces)) == 6
     with pytest.raises(ValueError):
         b.set_evals(torch.zeros(5))
-    with pytest.raises(NotImplementedError):
-        Problem("min", sphere, solution_length=3, num_actors=4)
+    with pytest.warns(UserWarning, match="no Ray actors"):  # accepted and mapped to this process / the torch.distributed ranks
+        assert Problem("min", sphere, solution_length=3, num_actors=4).num_actors == 0
     with pytest.raises(ValueError):
         Problem("sideways", sphere, solution_length=3)
     bounded = Problem("min", sphere, bounds=(-1, 1), solution_length=3, vectorized=True)
@@ -552,3 +552,64 @@ def test_values_and_evals_are_read_only_tensors():
     assert float(batch.values[0, 0]) == 0.5 and torch.isnan(batch.evals).all()
     x = torch.arange(3.0)
     assert storage_ptr(as_read_only_tensor(x)) == storage_ptr(x)
+
+
+# ---------------------------------------------------------------------------------------------- round 2: drop-in gaps
+@pytest.mark.parametrize("algo", ["snes", "pgpe", "cem"])
+def test_reference_quickstart_with_actors_and_distributed_runs_unchanged(algo):
+    """The reference's own quick-start (tests/test_examples.py:29-78) passes `num_actors=2` and `distributed=True`; with one
+    process that maps to the ordinary generation (a warning says so) and the status carries the same keys."""
+    def sphere1(x):
+        return torch.sum(x.pow(2.0))
+
+    with pytest.warns(UserWarning, match="no Ray actors"):
+        problem = Problem("min", sphere1, solution_length=10, initial_bounds=(-1, 1), num_actors=2)
+    kw = {"snes": (SNES, {"stdev_init": 5, "distributed": True}),
+          "pgpe": (PGPE, {"popsize": 10, "center_learning_rate": 0.01, "stdev_learning_rate": 0.1, "radius_init": 0.27, "distributed": True}),
+          "cem": (CEM, {"popsize": 10, "parenthood_ratio": 0.1, "radius_init": 0.27, "distributed": True})}[algo]
+    searcher = kw[0](problem, **kw[1])
+    searcher.run(2)
+    assert "center" in searcher.status and searcher.step_count == 2
+
+
+class _CountingProblem(Problem):
+    """A stand-in for an RL problem: every evaluated solution costs `cost` simulator interactions (vecgymne.py reports them
+    as the `total_interaction_count` status item)."""
+
+    def __init__(self, cost, **kw):
+        super().__init__("min", lambda x: torch.sum(x * x, dim=-1), initial_bounds=(-1, 1), solution_length=5, vectorized=True, seed=1, **kw)
+        self._cost, self._count = cost, 0
+
+    def _evaluate_batch(self, batch):
+        super()._evaluate_batch(batch)
+        self._count += self._cost * len(batch)
+
+    def _extra_status(self, batch):
+        return {"total_interaction_count": self._count}
+
+
+def test_adaptive_population_size_follows_the_reference_loop():
+    """gaussian.py:299-349: populations of `popsize` are sampled until MORE than `num_interactions` interactions were made
+    (or `popsize_max` solutions exist); the generation's population is their concatenation."""
+    prob = _CountingProblem(cost=3)
+    s = PGPE(prob, popsize=10, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0, num_interactions=100)
+    s.step()
+    assert len(s.population) == 40  # 10 solutions = 30 interactions; 30, 60, 90 are not > 100, 120 is
+    m0 = s.status["mean_eval"]
+    s.run(15)
+    assert len(s.population) == 40 and s.status["mean_eval"] < m0
+    capped = PGPE(_CountingProblem(cost=3), popsize=10, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0, num_interactions=100,
+                  popsize_max=20)
+    capped.run(2)
+    assert len(capped.population) == 20
+    with pytest.raises(ValueError):
+        PGPE(prob, popsize=10, center_learning_rate=0.1, stdev_learning_rate=0.1, stdev_init=1.0, popsize_max=20)
+    # the gradient service (core.py:3239-3282) with the same thresholds
+    prob2 = _CountingProblem(cost=3)
+    dist = SymmetricSeparableGaussian({"mu": torch.zeros(5), "sigma": torch.ones(5), "divide_mu_grad_by": "num_directions",
+                                       "divide_sigma_grad_by": "num_directions"})
+    prob2.evaluate(prob2.generate_batch(2))  # the status item exists from the first evaluation on
+    out = prob2.sample_and_compute_gradients(dist, 10, num_interactions=100, ranking_method="centered")[0]
+    assert out["num_solutions"] == 40 and set(out["gradients"]) == {"mu", "sigma"}
+    out = prob2.sample_and_compute_gradients(dist, 10, num_interactions=100, popsize_max=30, ranking_method="centered")[0]
+    assert out["num_solutions"] == 30
