@@ -33,8 +33,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "PGPE generations/sec at popsize=1Mxdim=10k (Rastrigin, fp32)"
+METRIC_BY_CONFIG = {"cfg2": "PGPE generations/sec at popsize=100kxdim=10k (Rastrigin, fp32)",
+                    "cfg5": "PGPE generations/sec at popsize=1Mxdim=100k sharded (Rastrigin, fp32)"}
 UNIT = "generations/s"
 LR_MU, LR_SIGMA, STDEV_INIT, SEED = 0.5, 0.1, 1.0, 0
+
+
+CONFIGS = {  # BASELINE.json configs that are bench workloads (the others are parity-test cases)
+    "metric": dict(popsize=1_000_000, dim=10_000),  # the configuration the metric is quoted on; fits one B200 (40 GB)
+    "cfg2": dict(popsize=100_000, dim=10_000),      # BASELINE configs[1]
+    "cfg5": dict(popsize=1_000_000, dim=100_000),   # BASELINE configs[4]: 400 GB of samples, sharded over 2 / 4 / 8 GPUs
+}
 
 
 def parse_args():
@@ -43,14 +52,32 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--popsize", type=int, default=1_000_000)
-    ap.add_argument("--dim", type=int, default=10_000)
-    ap.add_argument("--cpu-sample-popsize", type=int, default=2_000, help="population rows of the bounded CPU-baseline sample")
+    ap.add_argument("--config", default="metric", choices=sorted(CONFIGS), help="workload: metric = PGPE 1M x 10k (default); cfg2 = 100k x 10k; "
+                    "cfg5 = 1M x 100k row-sharded over the GPUs (materialised shards while they fit in HBM, else the lazy population)")
+    ap.add_argument("--popsize", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--lazy", type=int, default=-1, help="1/0: never materialise the population (Philox regeneration). Default: only when the shard does not fit")
+    ap.add_argument("--cpu-sizes", default=None, help="comma-separated population sizes of the CPU-baseline samples (default: 2k,4k,8k rows x 10k "
+                    "columns in our arm's bounded leg; 10k,30k,100k in the reference arm -- SURVEY 8(d))")
+    ap.add_argument("--cpu-budget-s", type=float, default=None, help="wall-clock budget of the CPU leg (default 25 s in our arm, 200 s in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cuda-graph", type=int, default=-1, help="1/0: replay each generation from a CUDA graph. Default: 0 at N = 1 (kernels are timed live inside the timed region), 1 at N > 1 (the captured graph includes the NCCL collectives: +5 %% at 2-8 GPUs; the fused kernel is then timed stand-alone right after the timed region)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg2 / cfg3 / cfg4 legs of the default N = 1 line")
+    ap.add_argument("--no-sharded-parity", action="store_true", help="skip the sharded-vs-unsharded parity leg at N > 1")
+    ap.add_argument("--cuda-graph", type=int, default=-1, help="1/0: replay each generation from a CUDA graph. Default: 0 at N = 1 (kernels are timed live inside the timed region), 1 at N > 1 (the fused kernel is then timed stand-alone right after the timed region)")
     ap.add_argument("--peer", type=int, default=-1, help="1/0: at N > 1 move fitnesses and gradients between the GPUs from inside the producing kernels (NVLink peer memory, evotorch_b200/peer.py) instead of NCCL all_gather/all_reduce. Default: 1 at N > 1")
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.popsize = cfg["popsize"] if a.popsize is None else a.popsize
+    a.dim = cfg["dim"] if a.dim is None else a.dim
+    return a
+
+
+def metric_name(args) -> str:
+    cfg = CONFIGS[args.config]
+    if (args.popsize, args.dim) == (cfg["popsize"], cfg["dim"]):
+        return METRIC_BY_CONFIG.get(args.config, METRIC)
+    return f"PGPE generations/sec at popsize={args.popsize}xdim={args.dim} (Rastrigin, fp32)"
 
 
 def workload_config(args, n_gpus, collectives="nccl"):
@@ -69,32 +96,57 @@ def workload_config(args, n_gpus, collectives="nccl"):
 
 
 # ----------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_run(args, steps: int, warmup: int) -> dict:
-    """Time the reference's torch-CPU op sequence on a bounded sample (popsize `cpu_sample_popsize`, full dim) with all host
-    threads, and scale linearly in popsize to the full workload (every op on the path is linear in N apart from the
-    O(N log N) argsort of N floats, which is < 1 % of a generation)."""
+def cpu_reference_run(args, *, sizes, budget_s: float, max_steps: int, with_gpu_eager: bool) -> dict:
+    """SURVEY 8(d) protocol for the reference's CPU path: time the reference's torch-CPU op sequence (oracle/ref_cpu_path.py,
+    bit-identical to the live reference) with all host threads at several population sizes (full dimension), check that the
+    time per generation is linear in the population size, and extrapolate to the workload's population from the least-squares
+    line t(N) = a + b N (every op on the path is linear in N apart from the O(N log N) argsort of N floats, < 1 % of a
+    generation).  `budget_s` bounds the leg: the number of timed generations per size is chosen from the first measurement."""
     import torch
 
     from oracle.ref_cpu_path import PGPEReferencePath
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_sample = min(args.cpu_sample_popsize, args.popsize)
-    n_sample -= n_sample % 2
-    path = PGPEReferencePath(args.dim, n_sample, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT, seed=SEED)
-    for _ in range(max(warmup, 1)):
-        path.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        path.step()
-    dt = time.perf_counter() - t0
-    sample_gps = steps / dt
-    full_gps = sample_gps * (n_sample / args.popsize)
+    sizes = sorted({min(int(n) - int(n) % 2, args.popsize) for n in sizes})
+    t_leg = time.perf_counter()
+    per_size, per_row_guess = [], None
+    share = budget_s / sum(sizes)  # seconds of budget per sampled row, all sizes together
+    for n in sizes:
+        path = PGPEReferencePath(args.dim, n, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT, seed=SEED)
+        path.step()  # generation 0 only samples and evaluates: allocation + first touch of the population, not timed
+        t0 = time.perf_counter()
+        path.step()  # first full generation (also the warm-up of the update ops)
+        first = time.perf_counter() - t0
+        per_row_guess = first / n
+        k = int(max(1, min(max_steps, (share * n - first) / max(first, 1e-9))))
+        times = []
+        for _ in range(k):
+            t0 = time.perf_counter()
+            path.step()
+            times.append(time.perf_counter() - t0)
+        times.sort()
+        per_size.append({"popsize": n, "timed_steps": k, "median_s": times[len(times) // 2], "min_s": times[0], "first_step_s": first})
+        del path
+    xs = [float(r["popsize"]) for r in per_size]
+    ys = [r["median_s"] for r in per_size]
+    if len(xs) >= 2:
+        mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+        b = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sum((x - mx) ** 2 for x in xs)
+        a = my - b * mx
+    else:
+        a, b = 0.0, ys[0] / xs[0]
+    resid = max(abs((a + b * x) - y) / y for x, y in zip(xs, ys))
+    t_full = a + b * args.popsize
+    prop = ys[-1] * args.popsize / xs[-1]  # plain proportional scaling of the largest sample, for comparison
+    linearity = {"fit": "t(N) = a + b*N seconds per generation, least squares over the medians", "a_s": a, "b_s_per_row": b,
+                 "max_rel_residual": resid, "extrapolated_s_per_generation": t_full, "proportional_from_largest_s": prop,
+                 "per_row_us": [1e6 * y / x for x, y in zip(xs, ys)]}
     torch_eager_gpu = None
-    if torch.cuda.is_available() and args.impl != "reference":
-        # the same torch op sequence, eager, on this GPU ("PyTorch path" comparator, SURVEY 8(d)); bounded sample, scaled like the CPU leg
+    if with_gpu_eager and torch.cuda.is_available():
+        # the same torch op sequence, eager, on this GPU ("PyTorch path" comparator, SURVEY 8(d)); bounded sample, scaled linearly
         try:
-            n_gpu = min(100_000, args.popsize)
+            n_gpu = min(100_000, args.popsize, int(1e9 // args.dim))
             n_gpu -= n_gpu % 2
             gpath = PGPEReferencePath(args.dim, n_gpu, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT, seed=SEED,
                                       device="cuda")
@@ -114,15 +166,26 @@ def cpu_reference_run(args, steps: int, warmup: int) -> dict:
         except Exception as exc:  # e.g. out of memory for the temporaries: report, do not fail the bench
             torch_eager_gpu = {"unavailable": repr(exc)[:200]}
     return {
-        "value": full_gps,
+        "value": 1.0 / t_full,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
+        "extrapolated": True,
+        "linearity": linearity,
+        "samples": per_size,
         "torch_eager_gpu": torch_eager_gpu,
-        "sample": f"{steps} generations at popsize={n_sample} x dim={args.dim} ({dt:.2f} s, {sample_gps:.4f} gen/s); "
-                  f"scaled linearly in popsize to {args.popsize}; torch {torch.__version__} CPU, {torch.get_num_threads()} threads",
-        "sample_ms_per_step": 1e3 * dt / steps,
+        "sample": ("generations of the reference's torch-CPU op sequence at popsize " + ", ".join(str(r["popsize"]) for r in per_size)
+                   + f" x dim={args.dim} (medians {', '.join('%.3f s' % r['median_s'] for r in per_size)}); least-squares line in popsize, "
+                   f"max residual {100 * resid:.1f} %, EXTRAPOLATED to popsize={args.popsize}; torch {torch.__version__} CPU, "
+                   f"{torch.get_num_threads()} threads; leg took {time.perf_counter() - t_leg:.0f} s"),
+        "sample_ms_per_step": 1e3 * ys[-1],
     }
+
+
+def cpu_sizes(args, default_elems) -> list:
+    if args.cpu_sizes:
+        return [int(x) for x in args.cpu_sizes.split(",") if x]
+    return [max(2, int(e // args.dim)) for e in default_elems]  # same element counts for any dimension
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -205,7 +268,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N, D, K, W = args.popsize, args.dim, args.steps, args.warmup
+    N, D, K, W = args.popsize, args.dim, args.steps, max(args.warmup, 3)
 
     def barrier_sync():
         if world > 1:
@@ -219,7 +282,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    problem = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=dev, seed=SEED)
+    # ---- does the shard fit?  materialised population = 4 N D / world bytes; else the lazy (Philox-regenerating) population
+    free_b, total_b = torch.cuda.mem_get_info()
+    shard_bytes = 4.0 * (N // world) * D
+    lazy = (shard_bytes > 0.85 * total_b) if args.lazy < 0 else bool(args.lazy)
+    if world > 1:  # every rank must take the same decision
+        t = torch.tensor([int(lazy)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lazy = bool(t.item())
+    problem = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=D, device=dev, seed=SEED, lazy_population=lazy)
     collectives, px = "nccl", None
     if world > 1 and (args.peer == 1 or args.peer < 0):
         try:
@@ -234,7 +305,7 @@ def run_ours(args):
     use_graph = (world > 1) if args.cuda_graph < 0 else args.cuda_graph == 1
     if use_graph:
         searcher.enable_cuda_graph()
-    for _ in range(max(W, 3)):
+    for _ in range(W):
         searcher.step()
 
     # ---- device-resident timing (value) + live per-kernel timing (roofline)
@@ -269,8 +340,8 @@ def run_ours(args):
         d0 = searcher._distribution
         ops.enable_timers()
         for _ in range(5):
-            ops.sample_eval(problem.evok_objective_id, pop._data, d0.mu, d0.sigma, n_rows=len(pop), symmetric=True, seed=1, stream_id=12345,
-                            f=pop._evdata.view(-1))
+            ops.sample_eval(problem.evok_objective_id, None if lazy else pop._data, d0.mu, d0.sigma, n_rows=len(pop), symmetric=True, seed=1,
+                            stream_id=12345, f=pop._evdata.view(-1))
         torch.cuda.synchronize()
         timers = dict(timers, **ops.timer_results())
         ops.disable_timers()
@@ -283,24 +354,29 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             cap = json.load(fh)["sample_eval"]
-        traffic = cap["ratio"] * fused_bytes
-        traffic_note = (f"dram__bytes_read+write = {cap['ratio']:.4f} x algorithmic bytes in {cap['source']} "
-                        f"(captured at popsize {cap['capture']['popsize']}, scaled linearly to this launch)")
+        if lazy:
+            traffic_note = "lazy population: the kernel stores nothing (fitnesses only); the figure is MODEL bandwidth (bytes a materialising kernel would write)"
+        else:
+            traffic = cap["ratio"] * fused_bytes
+            traffic_note = (f"dram__bytes_read+write = {cap['ratio']:.4f} x algorithmic bytes in {cap['source']} "
+                            f"(captured at popsize {cap['capture']['popsize']}, scaled linearly to this launch)")
     except Exception:
         pass
-    roofline = {"kernel": "evok::sample_eval_kernel<RASTRIGIN, symmetric, store, vec4>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "evok::sample_eval_kernel<RASTRIGIN, symmetric, %s, vec4>" % ("no store (lazy)" if lazy else "store"), "bound": "hbm",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
                 "timing": ("CUDA events around every launch inside the timed region" if not use_graph else
                            "generations replayed from a CUDA graph: the kernel was timed stand-alone (5 launches, CUDA events) right after the timed region"),
                 "share_of_step": fused_ms / (elapsed_ms / K)}
-    if "grad" in timers:
-        g_ms = timers["grad"][1]
-        g_bytes = 4.0 * (n_local // 2) * D
-        kern["grad"].update({"algorithmic_bytes": g_bytes, "achieved_gbs": g_bytes / (g_ms * 1e-3) / 1e9,
-                             "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peak})
+    for gname in ("grad", "grad_regen"):
+        if gname in timers:
+            g_ms = timers[gname][1]
+            g_bytes = 4.0 * (n_local // 2) * D
+            kern[gname].update({"algorithmic_bytes": g_bytes, "achieved_gbs": g_bytes / (g_ms * 1e-3) / 1e9,
+                                "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peak})
     model_bytes = 10.0 * n_local * D  # write X + read X (evaluate) + read the + rows (gradient)
-    traffic_bytes = 6.0 * n_local * D  # what this engine actually moves: evaluation is fused into the write
+    traffic_bytes = 0.0 if lazy else 6.0 * n_local * D  # what this engine actually moves: evaluation is fused into the write
 
     # ---- end to end: host-resident distribution -> device generation -> gradients back to the host, every step
     e2e = None
@@ -325,7 +401,7 @@ def run_ours(args):
             mu_host.copy_(upd.mu)
             sigma_host.copy_(new_sigma)
 
-        for _ in range(max(W, 3)):
+        for _ in range(W):
             e2e_step()
         barrier_sync()
         t0 = time.perf_counter()
@@ -338,6 +414,17 @@ def run_ours(args):
         e2e = {"value": K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms / K,
                "api": "Problem.sample_and_compute_gradients(host-resident SymmetricSeparableGaussian) + update_parameters/modify_tensor on the host"}
+    else:
+        del searcher
+        torch.cuda.empty_cache()
+
+    # ---- N > 1: parity of the sharded generation with the unsharded one (same seed), measured in this very run
+    sharded_parity = None
+    if world > 1 and not args.no_sharded_parity:
+        try:
+            sharded_parity = sharded_parity_leg(dev, use_peer=(px is not None))
+        except Exception as exc:
+            sharded_parity = {"error": repr(exc)[:300]}
 
     def finish():
         # leave without tearing the NCCL communicators down (teardown after graph-captured collectives can hang); every rank
@@ -355,38 +442,197 @@ def run_ours(args):
         return
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": elapsed_ms / K,
+        "metric": metric_name(args),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, world, collectives), cuda_graph=bool(use_graph)), "impl": "ours",
+        "config": dict(workload_config(args, world, collectives), cuda_graph=bool(use_graph), lazy_population=bool(lazy), name=args.config),
+        "impl": "ours",
         "gpu_launches": int(launches), "clocks": clock_info, "e2e": e2e, "roofline": roofline, "kernels": kern,
         "whole_generation": {"model_bytes_per_gen_per_gpu": model_bytes, "model_gbs": model_bytes * value / 1e9,
                              "model_frac_of_peak": model_bytes * value / 1e9 / peak,
                              "moved_bytes_per_gen_per_gpu": traffic_bytes, "moved_gbs": traffic_bytes * value / 1e9,
-                             "note": "model = SURVEY 8(d) 10*N*D bytes (unfused write+read+half read); moved = 6*N*D (evaluation fused into the sampling write)"},
+                             "note": "model = SURVEY 8(d) 10*N*D bytes (unfused write+read+half read); moved = 6*N*D (evaluation fused into the sampling write; 0 with the lazy population)"},
         "mean_eval_after": mean_eval,
     }
+    if sharded_parity is not None:
+        line["sharded_parity"] = sharded_parity
     if px is not None:
         if px.timed_out():
             raise RuntimeError("a peer-exchange wait timed out during the run: the numbers above are invalid")
         line["peer_exchange"] = {"wait_timeouts": 0, "buffer_bytes": px.nbytes}
+    if world == 1 and not args.no_other_configs and args.config == "metric":
+        line["other_configs"] = other_config_legs(dev, peak)
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference_run(args, steps=3, warmup=1)
+        line["cpu_baseline"] = cpu_reference_run(args, sizes=cpu_sizes(args, (2e7, 4e7, 8e7)), budget_s=args.cpu_budget_s or 25.0, max_steps=3,
+                                                 with_gpu_eager=True)
     emit(line)
     finish()
+
+
+def sharded_parity_leg(dev, use_peer: bool) -> dict:
+    """Three generations of PGPE at 100k x 1k, once row-sharded over the ranks (the collectives of the timed run) and once
+    unsharded on every rank, same seed: the first population's ranking must be IDENTICAL (same Philox counters, global
+    ranking) and mu / sigma must agree to fp32 summation order."""
+    import torch
+    import torch.distributed as dist
+
+    from evotorch_b200 import Problem, ops
+    from evotorch_b200.algorithms import PGPE
+    from evotorch_b200.objectives import rastrigin
+
+    n, d, gens, seed = 100_000, 1_000, 3, 17
+    world, rank = dist.get_world_size(), dist.get_rank()
+
+    def make(distributed):
+        prob = Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=d, device=dev, seed=seed)
+        if distributed and use_peer:
+            from evotorch_b200.peer import enable_peer_exchange
+
+            enable_peer_exchange(prob, n)
+        return prob, PGPE(prob, popsize=n, center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT, distributed=distributed)
+
+    prob_s, sh = make(True)
+    prob_u, un = make(False)
+    sh.step()
+    un.step()
+    # generation 0: the full fitness vector gathered by the sharded run vs the unsharded population's
+    px = getattr(prob_s, "_peer_exchange", None)
+    if px is not None:
+        f_sharded = px.f_all.clone()
+    else:
+        shard = next(iter(prob_s._grad_batches.values()))
+        parts = [torch.empty_like(shard.evals[:, 0]) for _ in range(world)]
+        dist.all_gather(parts, shard.evals[:, 0].contiguous())
+        f_sharded = torch.cat(parts)
+    f_un = un.population.evals[:, 0].contiguous()
+    p1 = torch.empty(n, dtype=torch.int64, device=dev)
+    p2 = torch.empty(n, dtype=torch.int64, device=dev)
+    ops.rank(f_sharded.contiguous(), "centered", False, perm=p1)
+    ops.rank(f_un, "centered", False, perm=p2)
+    fitness_equal = bool(torch.equal(f_sharded, f_un))
+    perm_equal = bool(torch.equal(p1, p2))
+    for _ in range(gens - 1):
+        sh.step()
+        un.step()
+
+    def rel(a, b):
+        return float(((a - b).abs() / (b.abs() + 1e-6)).max())
+
+    out = torch.tensor([rel(sh.status["center"], un.status["center"]), rel(sh.status["stdev"], un.status["stdev"]),
+                        0.0 if (fitness_equal and perm_equal) else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(out, op=dist.ReduceOp.MAX)
+    # every rank must also hold the SAME replicated distribution
+    c = sh.status["center"].clone()
+    c0 = c.clone()
+    dist.broadcast(c0, src=0)
+    same = torch.tensor([float(torch.equal(c, c0))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return {"workload": f"PGPE {n} x {d}, {gens} generations, seed {seed}: sharded over {world} ranks ({'peer exchange' if use_peer else 'NCCL'}) vs unsharded",
+            "max_rel_diff_mu": float(out[0]), "max_rel_diff_sigma": float(out[1]), "first_generation_fitness_and_permutation_identical": bool(out[2] == 0.0),
+            "replicated_state_identical_on_all_ranks": bool(same.item() == 1.0), "tolerance": 1e-5,
+            "ok": bool(out[0] < 1e-5 and out[1] < 1e-5 and out[2] == 0.0 and same.item() == 1.0)}
+
+
+def other_config_legs(dev, peak_gbs: float) -> dict:
+    """Short device-timed legs of the other single-GPU BASELINE configs (driver-timed with the headline line): cfg2 PGPE
+    100k x 10k, cfg3 CMA-ES D = 1024 popsize 4096 (sphere), cfg4 batched MLP(376-256-17) forward over 65 536 policies."""
+    import torch
+
+    from evotorch_b200 import Problem, ops
+    from evotorch_b200.algorithms import CMAES, PGPE
+    from evotorch_b200.objectives import rastrigin, sphere
+
+    out = {}
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    try:  # ---- cfg2
+        n, d = 100_000, 10_000
+        s = PGPE(Problem("min", rastrigin, initial_bounds=(-5.12, 5.12), solution_length=d, device=dev, seed=SEED), popsize=n,
+                 center_learning_rate=LR_MU, stdev_learning_rate=LR_SIGMA, stdev_init=STDEV_INIT)
+        for _ in range(3):
+            s.step()
+        ops.enable_timers()
+        ms = timed(s.step, 20)
+        tm = ops.timer_results()
+        ops.disable_timers()
+        se_ms = tm["sample_eval"][1]
+        out["cfg2_pgpe_100k_x_10k"] = {"generations_per_s": 1e3 / ms, "ms_per_step": ms, "steps": 20, "fused_kernel_ms": se_ms,
+                                       "fused_kernel_gbs": 4.0 * n * d / se_ms / 1e6, "fused_kernel_frac_of_hbm_peak": 4.0 * n * d / se_ms / 1e6 / peak_gbs,
+                                       "model_10ND_gbs": 10.0 * n * d / ms / 1e6}
+        s.enable_cuda_graph()
+        for _ in range(3):
+            s.step()
+        out["cfg2_pgpe_100k_x_10k"]["cuda_graph_generations_per_s"] = 1e3 / timed(s.step, 20)
+        del s
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["cfg2_pgpe_100k_x_10k"] = {"error": repr(exc)[:300]}
+    try:  # ---- cfg3
+        d, n = 1024, 4096
+        c = CMAES(Problem("min", sphere, initial_bounds=(-3, 3), solution_length=d, device=dev, seed=SEED), stdev_init=1.0, popsize=n)
+        for _ in range(5):
+            c.step()
+        ms = timed(c.step, 20)
+        flops = 2.0 * n * d * d * 2 + d**3 / 3.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                tf32_peak = float(json.load(fh)["bf16_tflops"]) / 2.0
+        except Exception:
+            tf32_peak = 1100.0
+        out["cfg3_cmaes_1024_x_4096"] = {"generations_per_s": 1e3 / ms, "ms_per_step": ms, "steps": 20, "useful_flop_per_generation": flops,
+                                         "useful_tflops": flops / ms / 1e9, "tensor_flop_per_generation_3xtf32": 3 * 2.0 * n * d * d * 2,
+                                         "frac_of_tf32_peak_3x": 3 * 2.0 * n * d * d * 2 / ms / 1e9 / tf32_peak, "tf32_peak_tflops": tf32_peak,
+                                         "mean_eval": float(c.status["mean_eval"])}
+        del c
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["cfg3_cmaes_1024_x_4096"] = {"error": repr(exc)[:300]}
+    try:  # ---- cfg4
+        from evotorch_b200.neuroevolution import Policy
+
+        net = torch.nn.Sequential(torch.nn.Linear(376, 256), torch.nn.Tanh(), torch.nn.Linear(256, 17))
+        pol = Policy(net)
+        NP = 65536
+        P = torch.empty(NP, pol.parameter_length, device=dev).normal_(0, 0.1)
+        obs = torch.randn(NP, 376, device=dev)
+        pol.set_parameters(P)
+        for _ in range(3):
+            pol(obs)
+        ms = timed(lambda: pol(obs), 10)
+        gb = 4.0 * NP * pol.parameter_length / 1e9
+        out["cfg4_mlp_376_256_17_x_65536"] = {"ms_per_forward": ms, "gbs": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / peak_gbs,
+                                              "observations_per_policy": 1, "activation": "tanh", "params_per_policy": pol.parameter_length}
+        del P, obs, pol
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["cfg4_mlp_376_256_17_x_65536"] = {"error": repr(exc)[:300]}
+    return out
 
 
 def run_reference(args):
     """The reference arm: the reference's own CPU implementation of the path (its torch-CPU op sequence, restated in
     oracle/ref_cpu_path.py and checked bit-identical against the real reference in the build container), all host threads,
-    same metric / config.  Rank 0 only."""
+    same metric / config, SURVEY 8(d) protocol: populations of 10k / 30k / 100k rows at the full dimension, linearity check,
+    extrapolation to the workload's population from the fitted line.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    base = cpu_reference_run(args, steps=max(1, min(args.steps, 5)), warmup=min(max(args.warmup, 1), 2))
+    base = cpu_reference_run(args, sizes=cpu_sizes(args, (1e8, 3e8, 1e9)), budget_s=args.cpu_budget_s or 200.0, max_steps=max(1, min(args.steps, 5)),
+                             with_gpu_eager=False)
     line = {
-        "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args), "value": base["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup,
         "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, n_gpus), "impl": "reference",
+        "data": "synthetic", "config": dict(workload_config(args, n_gpus), name=args.config), "impl": "reference",
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

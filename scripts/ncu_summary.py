@@ -66,8 +66,8 @@ def launch_shares(csv_path, out):
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
-for rep, name, title in (("prof_sample_eval", "ncu_sample_eval", "fused Philox sample + Rastrigin evaluate kernel (PGPE 200k x 10k)"),
-                         ("prof_grad", "ncu_grad", "TMA-staged weighted column reduction kernel (PGPE 200k x 10k)"),
+for rep, name, title in (("prof_sample_eval", "ncu_sample_eval", "fused Philox sample + Rastrigin evaluate kernel (PGPE 1M x 10k (metric size))"),
+                         ("prof_grad", "ncu_grad", "TMA-staged weighted column reduction kernel (PGPE 1M x 10k (metric size))"),
                          ("prof_scatter", "ncu_radix_scatter", "radix sort scatter pass (N = 1M keys)"),
                          ("prof_mlp", "ncu_mlp_forward", "batched MLP policy forward (65536 x 100881)"),
                          ("prof_gemm", "ncu_gemm_tf32x3", "tcgen05 3xTF32 GEMM, 4096 x 1024 x 1024 (CMA-ES Y = Z A^T)")):

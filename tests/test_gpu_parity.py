@@ -188,25 +188,30 @@ def test_cmaes_generation_at_config3_size_matches_oracle():
     A0 = np.linalg.cholesky(C0.astype(np.float64)).astype(np.float32)
     Z = rng.standard_normal((n, D), dtype=np.float32)
 
-    st = O.CMAESState(D, n, 1.0, m0)
-    st.C, st.A = C0.copy(), A0.copy()
-    Y, X = O.cmaes_sample(st, Z)
-    f = O.sphere(X)
-    aw = O.cmaes_assign_weights(st, f, "min")
-    O.cmaes_update(st, Z, Y, aw)
-
     prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=D, device=DEV, seed=3)
     c = CMAES(prob, stdev_init=1.0, popsize=n, center_init=C(m0))
     c.C, c.A = C(C0), C(A0)
-    close(N(c.weights), st.weights, rtol=2e-6, atol=1e-9)
     zt = C(Z)
     c.sample_distribution = _recorded_sampler(c, zt)
     c.step()
-    close(N(c.population.evals[:, 0]), f, rtol=2e-5)
+    f_ours = N(c.population.evals[:, 0])
+
+    st = O.CMAESState(D, n, 1.0, m0)
+    st.C, st.A = C0.copy(), A0.copy()
+    close(N(c.weights), st.weights, rtol=2e-6, atol=1e-9)
+    Y, X = O.cmaes_sample(st, Z)
+    close(N(c.population.values), X, rtol=2e-5, atol=2e-5)  # the sampling GEMM with its affine epilogue
+    close(f_ours, O.sphere(X), rtol=2e-5)
+    # both sides rank the same fitness vector: 4096 fitnesses of magnitude 1e4 are ~0.1 apart, so the 1e-6 relative difference
+    # between K2 and the float64 oracle swaps a few neighbouring ranks, and ONE swapped pair moves the recombination by 1e-6
+    # absolute -- the ranking itself is pinned bit-exactly elsewhere (feed the same f to both sides)
+    aw = O.cmaes_assign_weights(st, f_ours, "min")
+    O.cmaes_update(st, Z, Y, aw)
+
     close(N(c.m), st.m, rtol=2e-5, atol=3e-6)
     close(float(c.sigma), float(st.sigma), rtol=2e-5)
-    close(N(c.p_sigma), st.p_sigma, rtol=2e-5, atol=3e-6)
-    close(N(c.p_c), st.p_c, rtol=2e-5, atol=3e-6)
+    close(N(c.p_sigma), st.p_sigma, rtol=2e-5, atol=1e-5)  # = 27.8 (variance discount) x the fp32 weighted row sum
+    close(N(c.p_c), st.p_c, rtol=2e-5, atol=1e-5)
     scale = float(np.abs(st.C).max())
     assert float(np.abs(N(c.C).astype(np.float64) - st.C).max()) <= 2e-5 * scale
     assert float(np.abs(N(c.A).astype(np.float64) - st.A).max()) <= 2e-5 * float(np.abs(st.A).max())
