@@ -47,6 +47,58 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts[(int64_t)d * n_tiles + blockIdx.x] = h[d];
 }
 
+// Fused variant for few tiles (sharded ranking: N / world keys per GPU): the histogram kernel's LAST CTA also performs the
+// per-digit exclusive scan over the tiles (thread d owns digit d: n_tiles <= kFusedScanMaxTiles sequential adds), which
+// removes the digit_scan launch of every pass; with FIRST the kernel also builds the orderable keys / indices from the
+// fitnesses, which removes make_keys.  `done` is a zero-initialised counter that returns to zero.
+constexpr int kFusedScanMaxTiles = 256;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+    radix_hist_scan_kernel(const float* __restrict__ f, int descending, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, int64_t N, int shift,
+                           uint32_t* __restrict__ counts, int n_tiles, uint32_t* __restrict__ totals, unsigned int* done) {
+  __shared__ uint32_t h[kRadix];
+  __shared__ bool last;
+  for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+#pragma unroll
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const int64_t i = base + it * kSortThreads + threadIdx.x;
+    if (i < N) {
+      uint32_t k;
+      if (FIRST) {
+        k = orderable(f[i]);
+        if (descending) k = ~k;
+        keys[i] = k;
+        idx[i] = (uint32_t)i;
+      } else {
+        k = keys[i];
+      }
+      atomicAdd(&h[(k >> shift) & (kRadix - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts[(int64_t)d * n_tiles + blockIdx.x] = h[d];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  {  // kSortThreads == kRadix: thread d scans digit d over the tiles
+    uint32_t* row = counts + (int64_t)threadIdx.x * n_tiles;
+    uint32_t run = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const uint32_t c = __ldcg(row + t);
+      row[t] = run;
+      run += c;
+    }
+    totals[threadIdx.x] = run;
+  }
+  if (threadIdx.x == 0) *done = 0;
+}
+
 // per digit d (one CTA each): exclusive scan in place of counts[d][0..n_tiles) and the digit total.
 __global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ counts, int n_tiles, uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_tot[8];
@@ -367,13 +419,30 @@ static SortPlan make_plan(int64_t N) {
   return p;
 }
 
-// sorts; returns the device pointer (inside ws) of the sorted index array
-static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const SortPlan& p, cudaStream_t st, uint32_t** sorted_idx) {
+// sorts; returns the device pointer (inside ws) of the sorted index array (and of the sorted keys).
+// `fused_done` (nullable): a zero-initialised device counter; with it and few enough tiles the 13-launch pipeline shrinks to 8
+// (histogram + scan fused, keys made by the first histogram).
+static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const SortPlan& p, cudaStream_t st, uint32_t** sorted_idx,
+                      uint32_t** sorted_keys = nullptr, unsigned int* fused_done = nullptr) {
   char* base = (char*)ws;
   uint32_t* keys[2] = {(uint32_t*)(base + p.off_keys0), (uint32_t*)(base + p.off_keys1)};
   uint32_t* idx[2] = {(uint32_t*)(base + p.off_idx0), (uint32_t*)(base + p.off_idx1)};
   uint32_t* counts = (uint32_t*)(base + p.off_counts);
   uint32_t* totals = (uint32_t*)(base + p.off_totals);
+  if (fused_done && p.n_tiles <= kFusedScanMaxTiles) {
+    int cur = 0;
+    for (int pass = 0; pass < 32 / kRadixBits; ++pass) {
+      const int shift = pass * kRadixBits;
+      if (pass == 0) radix_hist_scan_kernel<true><<<p.n_tiles, kSortThreads, 0, st>>>(f, descending, keys[0], idx[0], N, shift, counts, p.n_tiles, totals, fused_done);
+      else radix_hist_scan_kernel<false><<<p.n_tiles, kSortThreads, 0, st>>>(nullptr, 0, keys[cur], nullptr, N, shift, counts, p.n_tiles, totals, fused_done);
+      radix_scatter_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
+      EVOK_CHECK_LAUNCH_N(2);
+      cur ^= 1;
+    }
+    *sorted_idx = idx[cur];
+    if (sorted_keys) *sorted_keys = keys[cur];
+    return 0;
+  }
   make_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f, N, descending, keys[0], idx[0]);
   EVOK_CHECK_LAUNCH();
   int cur = 0;
@@ -386,7 +455,122 @@ static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const
     cur ^= 1;
   }
   *sorted_idx = idx[cur];
+  if (sorted_keys) *sorted_keys = keys[cur];
   return 0;
+}
+
+// ---- sharded ranking over peer memory ----------------------------------------------------------------
+// Every GPU sorts only ITS OWN n_local fitnesses, pushes the sorted keys into every peer's key table (NVLink) and then
+// ranks its own rows against the world:  global position of a local element = its position in the local order
+//   + sum over the other shards s of  #{keys of s that precede it}   (upper bound for s < rank: equal keys of a lower
+//   shard have lower global indices and come first in the stable order; lower bound for s > rank).
+// Per GPU that is a sort of N / world keys plus n_local x (world - 1) binary searches over an L2-resident table instead
+// of a replicated sort of all N keys; the resulting positions (hence utilities) are bit-identical to the global sort.
+struct ShardTable {
+  long long off[EVOK_MAX_PEERS + 1];  // row offsets of the shards; off[world] = N
+};
+
+__global__ void __launch_bounds__(256)
+    rank_push_kernel(const uint32_t* __restrict__ sorted_keys, const float* __restrict__ f, int64_t n_local, int64_t my_off,
+                     const __grid_constant__ PeerSink keys_sink, const __grid_constant__ PeerSink fsum_sink, const unsigned long long* epoch,
+                     unsigned int* done) {
+  __shared__ double red[33];
+  const int world = keys_sink.world;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = sorted_keys[i];
+    for (int p = 0; p < world; ++p) static_cast<uint32_t*>(keys_sink.data[p])[my_off + i] = k;
+  }
+  if (blockIdx.x == 0) {  // deterministic local fitness sum (for the global mean_eval): one CTA, fixed order, double accumulation
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n_local; i += blockDim.x) acc += (double)f[i];
+    const double tot = block_sum<double>(acc, red);
+    if (threadIdx.x == 0)
+      for (int p = 0; p < world; ++p) static_cast<double*>(fsum_sink.data[p])[keys_sink.rank] = tot;
+  }
+  peer_signal_tail(keys_sink, epoch, done);
+}
+
+__device__ __forceinline__ unsigned long long rank_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+    rank_merge_kernel(const uint32_t* keys_all, const uint32_t* __restrict__ sorted_idx, const __grid_constant__ ShardTable tab, int world, int rank,
+                      int method, const float* __restrict__ nes_sum, const double* fsum, const unsigned long long* flags,
+                      unsigned long long* epoch, unsigned int* done, unsigned int* err, unsigned long long timeout_ns,
+                      float* __restrict__ w_local, float* __restrict__ mean_out) {
+  // wait until every rank's sorted keys have landed in the local table
+  const unsigned long long want = *epoch + 1ull;
+  if ((int)threadIdx.x < world) {
+    const unsigned long long t0 = rank_timer_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+      if (rank_timer_ns() - t0 > timeout_ns) {
+        atomicExch(err, 1u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const int64_t N = tab.off[world];
+  const int64_t my_off = tab.off[rank], n_local = tab.off[rank + 1] - my_off;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_local) {
+    const uint32_t key = __ldcg(keys_all + my_off + p);
+    // (world - 1) independent binary searches, advanced in lock step so that their L2 loads overlap
+    int64_t lo[EVOK_MAX_PEERS], hi[EVOK_MAX_PEERS];
+    int steps = 0;
+#pragma unroll
+    for (int s = 0; s < EVOK_MAX_PEERS; ++s) {
+      lo[s] = 0;
+      hi[s] = (s < world && s != rank) ? tab.off[s + 1] - tab.off[s] : 0;
+      int need = 0;
+      for (int64_t n = hi[s]; n > 0; n >>= 1) ++need;
+      steps = max(steps, need);
+    }
+    for (int it = 0; it < steps; ++it) {
+#pragma unroll
+      for (int s = 0; s < EVOK_MAX_PEERS; ++s) {
+        if (s < world && lo[s] < hi[s]) {
+          const int64_t mid = (lo[s] + hi[s]) >> 1;
+          const uint32_t k = __ldcg(keys_all + tab.off[s] + mid);
+          const bool before = s < rank ? (k <= key) : (k < key);  // does element `mid` of shard s precede ours?
+          if (before) lo[s] = mid + 1;
+          else hi[s] = mid;
+        }
+      }
+    }
+    int64_t pos = p;
+#pragma unroll
+    for (int s = 0; s < EVOK_MAX_PEERS; ++s)
+      if (s < world && s != rank) pos += lo[s];
+    float u;
+    if (method == EVOK_RANK_CENTERED) {
+      u = __fdiv_rn((float)pos, (float)(N - 1)) - 0.5f;
+    } else if (method == EVOK_RANK_LINEAR) {
+      u = __fdiv_rn((float)pos, (float)(N - 1));
+    } else {
+      const float Nf = (float)N;
+      const float t = fmaxf(0.0f, logf(Nf / 2.0f + 1.0f) - logf(Nf - (float)pos));
+      u = __fdiv_rn(t, *nes_sum) - __fdiv_rn(1.0f, Nf);
+    }
+    w_local[sorted_idx[p]] = u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && mean_out) {
+    double tot = 0.0;
+    for (int r = 0; r < world; ++r) tot += __ldcg(fsum + r);  // rank order: identical on every GPU
+    *mean_out = (float)(tot / (double)N);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {  // every CTA has read `epoch` before arriving here
+      *done = 0;
+      *epoch = want;
+    }
+  }
 }
 
 }  // namespace evok
@@ -472,6 +656,58 @@ extern "C" EVOK_API int evok_elite_mask(const float* w, int64_t N, int64_t num_e
   int rc = sort_pairs(w, N, /*descending=*/1, ws, p, st, &sidx);
   if (rc) return rc;
   elite_mask_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sidx, N, num_elites, mask);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_rank_sharded(int method, const float* f_local, int64_t N, int higher_is_better, int world, int rank,
+                                          const int64_t* row_offsets_host, void* const* peer_keys_host, void* const* peer_fsum_host,
+                                          void* const* peer_flags_host, uint64_t* epoch_dev, uint32_t* done_dev, uint32_t* err_dev,
+                                          uint64_t timeout_ns, float* w_local, float* mean_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!f_local || !row_offsets_host || !peer_keys_host || !peer_fsum_host || !peer_flags_host || !epoch_dev || !done_dev || !err_dev || !w_local || !ws)
+    return EVOK_E_NULLPTR;
+  if (method != EVOK_RANK_CENTERED && method != EVOK_RANK_LINEAR && method != EVOK_RANK_NES) return EVOK_E_BADENUM;
+  if (world < 1 || world > EVOK_MAX_PEERS || rank < 0 || rank >= world) return EVOK_E_BADSIZE;
+  if (N < 1 || N >= (int64_t)1 << 32 || row_offsets_host[0] != 0 || row_offsets_host[world] != N) return EVOK_E_BADSIZE;
+  ShardTable tab{};
+  for (int r = 0; r <= world; ++r) {
+    if (r > 0 && row_offsets_host[r] < row_offsets_host[r - 1]) return EVOK_E_BADSIZE;
+    tab.off[r] = row_offsets_host[r];
+  }
+  const int64_t my_off = tab.off[rank], n_local = tab.off[rank + 1] - my_off;
+  const SortPlan p = make_plan(n_local > 0 ? n_local : 1);
+  if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
+  PeerSink keys_sink{}, fsum_sink{};
+  keys_sink.world = fsum_sink.world = world;
+  keys_sink.rank = fsum_sink.rank = rank;
+  for (int q = 0; q < world; ++q) {
+    if (!peer_keys_host[q] || !peer_fsum_host[q] || !peer_flags_host[q]) return EVOK_E_NULLPTR;
+    keys_sink.data[q] = peer_keys_host[q];
+    fsum_sink.data[q] = peer_fsum_host[q];
+    keys_sink.flags[q] = fsum_sink.flags[q] = static_cast<unsigned long long*>(peer_flags_host[q]);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long* epoch = reinterpret_cast<const unsigned long long*>(epoch_dev);
+  uint32_t *sidx = nullptr, *skeys = nullptr;
+  if (n_local > 0) {
+    int rc = sort_pairs(f_local, n_local, !higher_is_better, ws, p, st, &sidx, &skeys, done_dev + 0);
+    if (rc) return rc;
+  }
+  int push_grid = (int)((n_local + 255) / 256);
+  if (push_grid > 2 * kNumSMs) push_grid = 2 * kNumSMs;
+  if (push_grid < 1) push_grid = 1;  // an empty shard still raises its flag
+  rank_push_kernel<<<push_grid, 256, 0, st>>>(skeys, f_local, n_local, my_off, keys_sink, fsum_sink, epoch, done_dev + 1);
+  EVOK_CHECK_LAUNCH();
+  float* scalar = (float*)((char*)ws + p.off_scalar);
+  if (method == EVOK_RANK_NES) {
+    nes_table_sum_kernel<<<1, 1024, 0, st>>>(N, scalar);
+    EVOK_CHECK_LAUNCH();
+  }
+  const unsigned merge_grid = (unsigned)((n_local + 255) / 256 > 0 ? (n_local + 255) / 256 : 1);
+  rank_merge_kernel<<<merge_grid, 256, 0, st>>>(static_cast<const uint32_t*>(peer_keys_host[rank]), sidx, tab, world, rank, method, scalar,
+                                               static_cast<const double*>(peer_fsum_host[rank]),
+                                               static_cast<const unsigned long long*>(peer_flags_host[rank]),
+                                               reinterpret_cast<unsigned long long*>(epoch_dev), done_dev + 2, err_dev, timeout_ns, w_local, mean_out);
   EVOK_CHECK_LAUNCH();
   return 0;
 }

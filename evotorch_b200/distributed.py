@@ -17,6 +17,7 @@ R-GPU run reproduces the single-GPU run at the same population size up to fp32 s
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -135,8 +136,13 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
             batch = cache[n_local] = SolutionBatch(problem, n_local, device=problem.device, empty=True)
         if peer is not None:  # the shard's fitness column IS its slice of the exchange buffer
             batch._evdata = peer.f_all[row0:row0 + n_local].view(n_local, 1)
+    sense = problem.senses[obj_index]
+    method = "raw" if ranking_method is None else ranking_method
+    # sharded ranking: sort locally, exchange sorted keys, rank the local rows against the world (no GPU holds all fitnesses)
+    sharded_rank = (peer is not None and method in ("centered", "linear", "nes") and dev_dist.accepts_local_weights(method)
+                    and os.environ.get("EVOTORCH_B200_SHARDED_RANK", "1") != "0")
     problem.philox_row0 = row0
-    problem._active_peer = peer
+    problem._active_peer = None if sharded_rank else peer  # sharded ranking: the fitnesses stay local (plain fused sampler)
     try:
         problem.sample_and_evaluate(dev_dist, batch)
     finally:
@@ -144,13 +150,31 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
         problem._active_peer = None
 
     samples = batch.recipe if isinstance(batch, LazySolutionBatch) else batch.access_values(keep_evals=True)
+    if sharded_rank:
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        scratch = problem.__dict__.setdefault("_grad_scratch", {})
+        w_local = scratch.get(n_local)
+        if w_local is None:
+            w_local = scratch[n_local] = torch.empty(n_local, dtype=torch.float32, device=problem.device)
+        w_local, mean_buf = peer.rank_sharded(batch._evdata.view(-1), method, sense == "max", offsets, w_local)
+        dev_dist._peer = peer
+        try:
+            summed = dev_dist.partial_gradients(samples, w_local, row0, method, local_weights_of=popsize)  # already summed over the ranks
+        finally:
+            dev_dist._peer = None
+        grads = dev_dist.finalize_gradients(summed, popsize)
+        mean_eval = mean_buf.reshape(())  # live 1-element buffer: holds the latest generation's global mean fitness
+        if home_device != problem.device:
+            grads = {k: v.to(home_device) for k, v in grads.items()}
+            mean_eval = mean_eval.to(home_device)
+        return {"gradients": grads, "num_solutions": popsize, "mean_eval": mean_eval}
     if peer is not None:
         f_all = peer.wait_fitness()
     else:
         f_local = batch.access_evals(obj_index)
         f_all = all_gather_rows(f_local.to(dev_dist.dtype), counts)
-    sense = problem.senses[obj_index]
-    method = "raw" if ranking_method is None else ranking_method
     weights_all = rank(f_all, method, higher_is_better=(sense == "max"))
 
     if peer is not None:

@@ -218,10 +218,11 @@ class SeparableGaussian(Distribution):
             make_gaussian(out=out, center=self.mu, stdev=self.sigma, symmetric=self.SYMMETRIC, generator=extract_generator(generator))
 
     # -------------------------------------------------- gradients (K4)
-    def _grad_scale(self, param_name: str, weights: torch.Tensor):
-        """divide_*_grad_by -> (host scale, optional device divisor) (distributions.py:517-536)."""
+    def _grad_scale(self, param_name: str, weights: torch.Tensor, n_total: Optional[int] = None):
+        """divide_*_grad_by -> (host scale, optional device divisor) (distributions.py:517-536).  `n_total`: the population
+        size when `weights` is only a shard's slice."""
         option = self.parameters.get(f"divide_{param_name}_grad_by")
-        n = weights.shape[0]
+        n = weights.shape[0] if n_total is None else int(n_total)
         if option is None:
             return 1.0, None
         if option == "num_solutions":
@@ -236,11 +237,13 @@ class SeparableGaussian(Distribution):
 
     def _prepared_weights(self, weights: torch.Tensor, ranking_used: Optional[str]) -> torch.Tensor:
         """`w - mean(w)` unless the ranking is already zero-centred (distributions.py:562-563, :722-723)."""
-        if ranking_used not in ("centered", "normalized"):
+        if ranking_used not in self._UNTOUCHED_RANKINGS:
             if ops.uses_kernels(weights):
                 return ops.weights_adjust_(weights.clone(), 1)
             return weights - torch.mean(weights)
         return weights
+
+    _UNTOUCHED_RANKINGS = ("centered", "normalized")  # utilities that `_prepared_weights` passes through unchanged
 
     def _weighted_sums(self, form: int, samples: torch.Tensor, w: torch.Tensor, scale_mu: float, scale_sigma: float) -> tuple:
         """(scale_mu * sum_r a_r eps_r, scale_sigma * sum_r b_r g(eps_r)) -- the K4 kernel, or its torch restatement."""
@@ -272,11 +275,32 @@ class SeparableGaussian(Distribution):
             g = ((eps**2) - (sigma**2)) / sigma
         return _weighted_colsum(a, eps) * scale_mu, _weighted_colsum(b, g) * scale_sigma
 
-    def partial_gradients(self, samples: torch.Tensor, all_weights: torch.Tensor, row0: int, ranking_used: Optional[str]) -> dict:
+    def accepts_local_weights(self, ranking_used: Optional[str]) -> bool:
+        """True when a shard's gradient contribution needs nothing but the utilities of its OWN rows (no statistic of the whole
+        utility vector: no mean subtraction, no sum / stdev divisor, no elite selection) -- the condition for the sharded
+        ranking, where no GPU ever holds the full utility vector."""
+        if "parenthood_ratio" in self.parameters:
+            return False
+        for name in ("mu", "sigma"):
+            if self.parameters.get(f"divide_{name}_grad_by") not in (None, "num_solutions", "num_directions"):
+                return False
+        return ranking_used in self._UNTOUCHED_RANKINGS and ranking_used in ("centered", "linear", "nes")
+
+    def partial_gradients(self, samples: torch.Tensor, all_weights: torch.Tensor, row0: int, ranking_used: Optional[str],
+                          local_weights_of: Optional[int] = None) -> dict:
         """Gradient contribution of a row shard.  `samples` are rows [row0, row0 + n) of a population whose utilities are
         `all_weights` (ranked over the WHOLE population).  The dictionaries of all shards add up (all-reduce) to what
-        `finalize_gradients` turns into the result of `compute_gradients` on the whole population."""
+        `finalize_gradients` turns into the result of `compute_gradients` on the whole population.
+        `local_weights_of=N`: `all_weights` holds only the utilities of THIS shard's rows, of a population of N solutions
+        (sharded ranking; see `accepts_local_weights`)."""
         n_local = samples.shape[0]
+        if local_weights_of is not None:
+            if not self.accepts_local_weights(ranking_used):
+                raise ValueError("this distribution / ranking needs the utilities of the whole population")
+            smu, _ = self._grad_scale("mu", all_weights, local_weights_of)
+            ssig, _ = self._grad_scale("sigma", all_weights, local_weights_of)
+            gmu, gsig = self._weighted_sums(self.GRAD_FORM, samples, all_weights, smu, ssig)
+            return {"mu": gmu, "sigma": gsig}
         if "parenthood_ratio" in self.parameters:  # CEM elite moments (distributions.py:538-546)
             num_elites = math.floor(all_weights.shape[0] * self.parameters["parenthood_ratio"])
             if ops.uses_kernels(all_weights):
@@ -349,6 +373,8 @@ class ExpSeparableGaussian(SeparableGaussian):
                 return ops.weights_adjust_(weights.clone(), 2)
             return weights / torch.sum(torch.abs(weights))
         return weights
+
+    _UNTOUCHED_RANKINGS = ("nes",)
 
     def update_parameters(self, gradients: dict, *, learning_rates: Optional[dict] = None, optimizers: Optional[dict] = None):
         """mu + follow(grad_mu); sigma * exp(0.5 * follow(grad_sigma)) (distributions.py:795-810)."""

@@ -45,7 +45,8 @@ def _align(n: int, a: int = 256) -> int:
 
 
 class PeerExchange:
-    """The exchange buffer of this rank, mapped by all peers:  [ f_all : N f32 | slots : R x 2D f32 | flags_f : R u64 | flags_g : R u64 ]."""
+    """The exchange buffer of this rank, mapped by all peers:
+    [ f_all : N f32 | slots : R x 2D f32 | flags_f : R u64 | flags_g : R u64 | keys_all : N u32 | fsum : R f64 ]."""
 
     def __init__(self, popsize: int, solution_length: int, device: torch.device, *, timeout_ns: int = DEFAULT_TIMEOUT_NS):
         if not (dist.is_available() and dist.is_initialized()):
@@ -60,7 +61,9 @@ class PeerExchange:
         self._off_slots = _align(4 * n)
         self._off_flags_f = self._off_slots + _align(4 * r * 2 * d)
         self._off_flags_g = self._off_flags_f + _align(8 * r)
-        self.nbytes = self._off_flags_g + _align(8 * r)
+        self._off_keys = self._off_flags_g + _align(8 * r)      # sharded ranking: N sorted orderable keys (u32), shard by shard
+        self._off_fsum = self._off_keys + _align(4 * n)         # ... and one local fitness sum (f64) per rank
+        self.nbytes = self._off_fsum + _align(8 * r)
 
         lib = nat.lib()
         with torch.cuda.device(self.device):
@@ -83,6 +86,7 @@ class PeerExchange:
 
         self.peer_f, self.peer_slots = table(self._off_f), table(self._off_slots)
         self.peer_flags_f, self.peer_flags_g = table(self._off_flags_f), table(self._off_flags_g)
+        self.peer_keys, self.peer_fsum = table(self._off_keys), table(self._off_fsum)
         # local views
         self.f_all = _view(self._base + self._off_f, n, "<f4", self.device)
         self.slots = _view(self._base + self._off_slots, r * 2 * d, "<f4", self.device)
@@ -90,6 +94,8 @@ class PeerExchange:
         # local (unshared) state: [epoch_f, epoch_g] u64, [done_f, done_g, done_r, err] u32
         self._epochs = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._counters = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._rank_counters = torch.zeros(4, dtype=torch.int32, device=self.device)  # sharded ranking: hist-scan / push / merge
+        self._mean_eval = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.reduced = torch.empty(2 * d, dtype=torch.float32, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier()  # nobody writes into a peer before that peer has zeroed and published its buffer
@@ -111,6 +117,23 @@ class PeerExchange:
         nat.check(nat.lib().evok_peer_wait(self._flags_f_ptr, self.world, self.epoch_f, self._counter(3), self.timeout_ns,
                                            nat.stream_of(self.f_all)), "evok_peer_wait")
         return self.f_all
+
+    def rank_sharded(self, f_local: torch.Tensor, method: str, higher_is_better: bool, row_offsets: list, w_local: torch.Tensor) -> tuple:
+        """Sharded ranking (evok_rank_sharded): local sort -> sorted keys pushed to every peer -> global position of every LOCAL
+        row by binary search over the peers' sorted shards.  Takes the place of `wait_fitness()` + the replicated global rank
+        (it uses the same flag set / epoch as the fitness gather: a generation does one or the other).  Returns the utilities of
+        the local rows (`w_local`, in local row order) and the global mean fitness (a 1-element device tensor)."""
+        from . import ops
+
+        lib = nat.lib()
+        n_local = f_local.numel()
+        offs = (ctypes.c_int64 * (self.world + 1))(*row_offsets)
+        ws = nat.workspace(self.device, lib.evok_rank_workspace_bytes(max(n_local, 1)), "rank_sharded")
+        nat.check(lib.evok_rank_sharded(ops.RANK_IDS[method], f_local.data_ptr(), self.popsize, int(bool(higher_is_better)), self.world, self.rank,
+                                        offs, self.peer_keys, self.peer_fsum, self.peer_flags_f, self.epoch_f, self._rank_counters.data_ptr(),
+                                        self._counter(3), self.timeout_ns, w_local.data_ptr(), self._mean_eval.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), nat.stream_of(f_local)), "evok_rank_sharded")
+        return w_local, self._mean_eval
 
     def reduce_gradients(self) -> tuple:
         """Wait for every rank's slot, sum them in rank order -> (grad_mu, grad_sigma) views of `self.reduced`."""

@@ -234,6 +234,21 @@ int evok_transpose_scale(const float* in, int64_t ldi, int64_t rows, int64_t col
  * `done_dev` is a zero-initialised local uint32 per exchange point; `epoch_dev` a zero-initialised local uint64 per
  * exchange point.  Everything is stream-ordered and CUDA-graph capturable (the pointers are baked into the launch).
  * --------------------------------------------------------------------------------------------- */
+/* Sharded ranking (round 2): the fitness all-gather + replicated global sort of the sharded generation replaced by a LOCAL
+ * sort + an exchange of sorted keys.  Each GPU sorts only its own n_local fitnesses (stable LSD radix, 8 launches), pushes the
+ * sorted orderable keys into every peer's key table (peer_keys_host[p] = base of peer p's N-entry uint32 table) together with
+ * its local fitness sum (peer_fsum_host[p] = base of peer p's `world` doubles) and raises its flag; then, after all flags have
+ * arrived, every local row finds its GLOBAL position = local position + sum over the other shards of the number of their keys
+ * that precede it (binary searches over the L2-resident table; ties by global index exactly like the global stable sort) and
+ * writes its utility.  Replaces, per GPU, tools/ranking.py:24-124 on the all-gathered vector (the Ray path ranks per actor,
+ * core.py:3289).  Results are bit-identical to evok_rank on the gathered vector; methods: CENTERED, LINEAR, NES.
+ * row_offsets_host: world + 1 global row offsets of the shards (host array); w_local: n_local utilities in local row order;
+ * mean_out (nullable): global mean fitness.  done_dev: THREE zero-initialised uint32; ws: evok_rank_workspace_bytes(n_local). */
+int evok_rank_sharded(int method, const float* f_local, int64_t N, int higher_is_better, int world, int rank,
+                      const int64_t* row_offsets_host, void* const* peer_keys_host, void* const* peer_fsum_host,
+                      void* const* peer_flags_host, uint64_t* epoch_dev, uint32_t* done_dev, uint32_t* err_dev, uint64_t timeout_ns,
+                      float* w_local, float* mean_out, void* ws, size_t ws_bytes, void* stream);
+
 int evok_peer_alloc(size_t bytes, void** dev_ptr_out_host, void* handle_out_64B_host);
 int evok_peer_open(const void* handle_64B_host, void** dev_ptr_out_host);
 int evok_peer_close(void* dev_ptr);

@@ -298,3 +298,69 @@ def test_captured_graph_owns_its_workspaces():
         for j in junk:
             j.fill_(float("nan"))
     assert torch.equal(eager.status["center"], graph.status["center"]) and torch.equal(eager.status["stdev"], graph.status["stdev"])
+
+
+# ------------------------------------------------------------------------------------------------ sharded ranking
+@pytest.mark.parametrize("method", ["centered", "linear", "nes"])
+@pytest.mark.parametrize("hib", [False, True])
+@pytest.mark.parametrize("counts", [[5000, 3000, 4096, 2], [2048, 2048], [7, 0, 12001, 30, 1, 600, 2, 2050], [20000]])
+def test_sharded_ranking_is_bit_identical_to_the_global_sort(method, hib, counts):
+    """evok_rank_sharded with `world` simulated ranks on one GPU (one stream and one set of exchange buffers per rank, all
+    resident on this device): every rank sorts only its shard, the sorted keys are exchanged, and the utilities of the local
+    rows must equal -- bit for bit -- the slice of the global ranking (K3 on the concatenated vector; stable ties by global
+    index, NaN largest, -0 == +0)."""
+    import ctypes
+
+    from evotorch_b200 import _native as nat
+
+    lib = nat.lib()
+    R, n = len(counts), sum(counts)
+    g = torch.Generator(device=DEV).manual_seed(n + R)
+    f = torch.randn(n, device=DEV, generator=g)
+    f = torch.round(f * 50) / 50  # massive ties, within and across shards
+    f[::97] = float("nan")
+    f[5::101] = -0.0
+    f[6::101] = 0.0
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    want = ops.rank(f.contiguous(), method, hib)
+    keys = [torch.zeros(n, dtype=torch.int32, device=DEV) for _ in range(R)]
+    fsum = [torch.zeros(R, dtype=torch.float64, device=DEV) for _ in range(R)]
+    flags = [torch.zeros(R, dtype=torch.int64, device=DEV) for _ in range(R)]
+    epoch = [torch.zeros(1, dtype=torch.int64, device=DEV) for _ in range(R)]
+    done = [torch.zeros(4, dtype=torch.int32, device=DEV) for _ in range(R)]
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    w = [torch.full((max(c, 1),), 7.0, device=DEV) for c in counts]
+    mean = [torch.zeros(1, device=DEV) for _ in range(R)]
+    ws = [torch.empty(lib.evok_rank_workspace_bytes(max(c, 1)), dtype=torch.uint8, device=DEV) for c in counts]
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    tab = lambda ts: (ctypes.c_void_p * R)(*[t.data_ptr() for t in ts])
+    c_offs = (ctypes.c_int64 * (R + 1))(*offs)
+    torch.cuda.synchronize()
+    for rounds in range(2):  # twice: the epochs / counters must come back ready for the next generation
+        for r in range(R):
+            fl = f[offs[r]:offs[r + 1]].contiguous() if counts[r] else torch.zeros(1, device=DEV)
+            with torch.cuda.stream(streams[r]):
+                rc = lib.evok_rank_sharded(ops.RANK_IDS[method], fl.data_ptr(), n, int(hib), R, r, c_offs, tab(keys), tab(fsum), tab(flags),
+                                           epoch[r].data_ptr(), done[r].data_ptr(), err.data_ptr(), int(5e9), w[r].data_ptr(), mean[r].data_ptr(),
+                                           ws[r].data_ptr(), ws[r].numel(), streams[r].cuda_stream)
+            assert rc == 0
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        for r in range(R):
+            assert torch.equal(w[r][:counts[r]].view(torch.int32), want[offs[r]:offs[r + 1]].view(torch.int32)), (r, rounds)
+            assert int(epoch[r].item()) == rounds + 1 and int(done[r].abs().sum().item()) == 0
+    finite = f[torch.isfinite(f)]
+    # the global mean is the same number on every rank (NaN here, because the vector holds NaNs; check the mechanism on a clean one)
+    f2 = torch.randn(n, device=DEV, generator=g) + 3.0
+    for r in range(R):
+        fl = f2[offs[r]:offs[r + 1]].contiguous() if counts[r] else torch.zeros(1, device=DEV)
+        with torch.cuda.stream(streams[r]):
+            lib.evok_rank_sharded(ops.RANK_IDS[method], fl.data_ptr(), n, int(hib), R, r, c_offs, tab(keys), tab(fsum), tab(flags), epoch[r].data_ptr(),
+                                  done[r].data_ptr(), err.data_ptr(), int(5e9), w[r].data_ptr(), mean[r].data_ptr(), ws[r].data_ptr(), ws[r].numel(),
+                                  streams[r].cuda_stream)
+    torch.cuda.synchronize()
+    assert all(torch.equal(mean[0], m) for m in mean)
+    close(float(mean[0]), float(f2.double().mean()), rtol=1e-6)
+    del finite

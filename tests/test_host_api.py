@@ -306,7 +306,8 @@ def test_bench_reference_arm_prints_one_json_line():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--cpu-sample-popsize", "64", "--dim", "200", "--popsize", "1000"], capture_output=True, text=True, timeout=300)
+                        "--cpu-sizes", "64,128,256", "--cpu-budget-s", "2", "--dim", "200", "--popsize", "1000"], capture_output=True, text=True,
+                       timeout=300)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -315,6 +316,9 @@ def test_bench_reference_arm_prints_one_json_line():
                 "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    lin = d["cpu_baseline"]["linearity"]  # several population sizes, a fitted line, its residual, an extrapolated value
+    assert [r["popsize"] for r in d["cpu_baseline"]["samples"]] == [64, 128, 256] and lin["max_rel_residual"] >= 0
+    assert abs(1.0 / lin["extrapolated_s_per_generation"] - d["value"]) < 1e-9 * d["value"] and d["cpu_baseline"]["extrapolated"] is True
 
 
 # ------------------------------------------------------------------------------------------------ pickling / checkpoints
