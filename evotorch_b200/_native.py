@@ -28,6 +28,9 @@ _SIGNATURES = {
     "evok_rank_workspace_bytes": (c_size_t, [c_int64]),
     "evok_rank": (c_int, [c_int, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
     "evok_argsort": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "evok_rank_table": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
+    "evok_cmaes_row_weights": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
+    "evok_cmaes_vector_update": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, c_int, _P, _P, _P]),
     "evok_weights_adjust": (c_int, [_P, c_int64, c_int, _P]),
     "evok_elite_mask": (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "evok_grad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
@@ -46,6 +49,8 @@ _SIGNATURES = {
                                       c_size_t, _P]),
     "evok_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "evok_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "evok_gemm_nt_affine": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "evok_transpose_pair": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P]),
     "evok_transpose_scale": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "evok_peer_alloc": (c_int, [c_size_t, _P, _P]),
     "evok_peer_open": (c_int, [_P, _P]),

@@ -9,12 +9,16 @@ Per generation (cmaes.py:567-606):
 The rank-mu term is computed as Y^T diag(w) Y (a weighted SYRK): the reference materialises an N x D x D broadcast
 temporary (cmaes.py:548; 16 GiB at D = 1024, N = 4096).  On CUDA fp32 both contractions run on the hand-written tcgen05
 kernel (csrc/evok_gemm.cu: TMA -> 128B-swizzled smem -> tcgen05.mma.kind::tf32 with 3xTF32 operand splitting -> TMEM ->
-register accumulation); the Cholesky factorisation stays on cuSOLVER (torch.linalg.cholesky).
+register accumulation; the lo halves of the 3xTF32 operands are derived inside the kernel, so operands are read from HBM once); the
+glue between the contractions is fused into four small kernels (csrc/evok_cmaes.cu, evok_rank_table) and the covariance update is
+applied by the SYRK's epilogue, so a generation is ~14 launches with no host reads and replays from a CUDA graph
+(`enable_cuda_graph()`).  The Cholesky factorisation stays on cuSOLVER (torch.linalg.cholesky_ex).
 """
 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -118,6 +122,7 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             self.decompose_C_freq = max(1, int(np.floor(_safe_divide(1, 10 * d * (self.c_1 + self.c_mu)))))
         else:
             self.decompose_C_freq = 1
+        self._use_graph, self._graph = os.environ.get("EVOTORCH_B200_CUDA_GRAPH", "0") == "1", None
         SinglePopulationAlgorithmMixin.__init__(self)
 
     # ------------------------------------------------------------------ accessors
@@ -130,7 +135,7 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         return self._obj_index
 
     def _get_center(self) -> torch.Tensor:
-        return self.m
+        return self.m.clone() if self.__dict__.get("_fused") is not None else self.m  # the fused step updates `m` in place
 
     def _get_sigma(self) -> float:
         return float(self.sigma)
@@ -141,19 +146,22 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
         n = self.popsize if num_samples is None else int(num_samples)
         problem = self._problem
         d = problem.solution_length
-        zs = problem.make_empty(num_solutions=n)
+        fs = self.__dict__.get("_fused") if n == self.popsize else None  # persistent buffers of the fused generation
+        zs = problem.make_empty(num_solutions=n) if fs is None else fs["zs"]
         if ops.uses_kernels(zs) and problem.rng == "philox":
             seed, stream_id = problem.next_philox_stream()
-            zero, one = problem.make_zeros(d), problem.make_ones(d)
-            ops.sample_eval(ops.OBJ_NONE, zs, zero, one, n_rows=n, symmetric=False, seed=seed, stream_id=stream_id)
+            zero, one = (problem.make_zeros(d), problem.make_ones(d)) if fs is None else (fs["zero"], fs["one"])
+            ops.sample_eval(ops.OBJ_NONE, zs, zero, one, n_rows=n, symmetric=False, seed=seed, stream_id=stream_id,
+                            stream_offset=problem.philox_stream_offset)
         else:
             problem.make_gaussian(out=zs)
         if self.separable:
             ys = self.A.unsqueeze(0) * zs
         elif ops.uses_kernels(zs) and ops.uses_kernels(self.A):
-            # K6: one tcgen05 GEMM (3xTF32, fp32-accurate) with the affine epilogue xs = m + sigma * ys fused in
-            ys = torch.empty_like(zs)
-            xs = torch.empty_like(zs)
+            # K6: one tcgen05 GEMM (3xTF32, fp32-accurate) with the affine epilogue xs = m + sigma * ys fused in; in the fused
+            # generation xs IS the population's value buffer
+            ys = torch.empty_like(zs) if fs is None else fs["ys"]
+            xs = torch.empty_like(zs) if fs is None else self._population._data
             ops.gemm_nt(zs, self.A.contiguous(), ys, out2=xs, alpha=self.sigma.reshape(1), bias=self.m.contiguous())
             return zs, ys, xs
         else:
@@ -244,7 +252,120 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
     def decompose_C(self) -> None:
         self.A = self.C.pow(0.5) if self.separable else torch.linalg.cholesky(self.C)
 
+    # ------------------------------------------------------------------ fused generation (CUDA float32, full covariance)
+    def _fused_ok(self) -> bool:
+        return (not self.separable and self.stdev_min is None and self.stdev_max is None and ops.uses_kernels(self.m) and ops.uses_kernels(self.C)
+                and self._problem.rng == "philox" and self._population._data.is_contiguous()
+                and self._population._evdata.shape[1] == 1 and self._population._evdata.dtype == torch.float32)
+
+    def _fused_state(self) -> dict:
+        fs = self.__dict__.get("_fused")
+        if fs is None:
+            p, n, d = self._problem, self.popsize, self._problem.solution_length
+            dev = self.m.device
+            new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+            fs = self._fused = dict(zs=new(n, d), ys=new(n, d), aw=new(n), w_pos=new(n), w_act=new(n), local=new(d), shaped=new(d), scratch=new(d),
+                                    k=new(3), zero=p.make_zeros(d), one=p.make_ones(d), info=torch.zeros((), dtype=torch.int32, device=dev),
+                                    steps_dev=None)
+            # state tensors become persistent buffers that the kernels update in place (pointer-stable: CUDA-graph replay)
+            self.m, self.p_sigma, self.p_c = self.m.contiguous().clone(), self.p_sigma.contiguous().clone(), self.p_c.contiguous().clone()
+            self.sigma = self.sigma.reshape(()).clone()
+            self.C, self.A = self.C.contiguous().clone(), self.A.contiguous().clone()
+            self._consts = (self.c_m, self.c_sigma, self.damp_sigma, self.c_c, self.c_1, self.c_mu, self.variance_discount_sigma,
+                            self.variance_discount_c, float(self.unbiased_expectation), self._weights_sum)
+        return fs
+
+    def _step_fused(self):
+        """One generation as a short chain of kernels with no host reads (cmaes.py:567-606):
+        K1 z-sampling -> GEMM (Y = Z A^T, X = m + sigma Y straight into the population) -> evaluate -> rank-to-weights (K3, one launch)
+        -> row weights (positive part / active reweighting, one pass over Z) -> two weighted row sums (K4) -> fused vector update
+        (m, p_sigma, sigma, h_sig, p_c + the covariance coefficients) -> weighted SYRK with the covariance update in its epilogue ->
+        Cholesky.  Every state tensor is updated in place."""
+        fs = self._fused_state()
+        zs, ys, xs = self.sample_distribution()
+        pop = self._population
+        if xs.data_ptr() == pop._data.data_ptr():
+            pop._evdata.fill_(float("nan"))
+        else:  # an overriding `sample_distribution` (e.g. recorded draws in the tests) returns its own tensors
+            pop.set_values(xs)
+        self._problem.evaluate(pop)
+        f = pop._evdata.view(-1)
+        ops.rank_table(f, self._problem.senses[self._obj_index] == "max", self.weights, out=fs["aw"])
+        ops.cmaes_row_weights(fs["aw"], zs, self.active, fs["w_pos"], fs["w_act"])
+        ops.grad(ops.GRAD_MOMENTS, zs, fs["w_pos"], fs["zero"], fs["one"], 1.0, 1.0, out_mu=fs["local"], out_sigma=fs["scratch"])
+        ops.grad(ops.GRAD_MOMENTS, ys, fs["w_pos"], fs["zero"], fs["one"], 1.0, 1.0, out_mu=fs["shaped"], out_sigma=fs["scratch"])
+        ops.cmaes_vector_update(fs["local"], fs["shaped"], self.m, self.p_sigma, self.p_c, self.sigma, self._consts, self.csa_squared, fs["k"],
+                                steps=self._steps_count, steps_dev=fs["steps_dev"])
+        ops.weighted_syrk_update(ys, fs["w_act"], fs["k"], self.C, u=self.p_c, out=self.C)
+        if fs["steps_dev"] is not None or (self._steps_count + 1) % self.decompose_C_freq == 0:
+            torch.linalg.cholesky_ex(self.C, check_errors=False, out=(self.A, fs["info"]))
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the fused generation
+    def enable_cuda_graph(self, enabled: bool = True):
+        """Capture the fused generation into a CUDA graph and replay it from `step()` (one graph launch per generation; the
+        z-sampler reads a device-side generation counter, `_h_sig` a device-side step counter, so the replayed trajectory equals
+        eager stepping).  Used when the configuration is capturable: fused path, built-in objective, no evaluation hooks, Cholesky
+        every generation (`decompose_C_freq == 1`); otherwise stepping stays eager."""
+        self._use_graph = bool(enabled)
+        self._graph = None
+        return self
+
+    def _graph_capturable(self) -> bool:
+        prob = self._problem
+        return (self._fused_ok() and self.decompose_C_freq == 1 and prob.evok_objective_id is not None and len(prob.before_eval_hook) == 0
+                and len(prob.after_eval_hook) == 0 and not prob.stores_solution_stats and "sample_distribution" not in self.__dict__)
+
+    def _step_graph(self):
+        from .. import _native as nat
+
+        prob = self._problem
+        if self._graph is None:
+            self._step_fused()  # warm every kernel / workspace / cuSOLVER handle eagerly, right before the capture
+            fs = self._fused_state()
+            prob.philox_stream_offset = torch.zeros(1, dtype=torch.int32, device=self.m.device)
+            fs["steps_dev"] = torch.full((1,), self._steps_count + 1, dtype=torch.int64, device=self.m.device)
+            base = prob._philox_stream
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
+            try:
+                with nat.private_workspaces() as store, torch.cuda.graph(graph):
+                    self._step_fused()
+                    prob.philox_stream_offset.add_(1)
+            except Exception:  # e.g. a library call inside the step that cannot be captured on this build: stay eager
+                prob.philox_stream_offset, fs["steps_dev"] = None, None
+                prob._philox_stream = base
+                self._use_graph = False
+                torch.cuda.synchronize()
+                return
+            self._graph_kernels = ops.launch_count() - before
+            ops.count_replayed_launches(-self._graph_kernels)
+            prob._philox_stream = base  # the capture consumed a host-side stream id without running anything
+            prob.philox_stream_offset.zero_()
+            self._graph, self._graph_workspaces = graph, store
+            return
+        self._graph.replay()
+        ops.count_replayed_launches(self._graph_kernels)
+        prob._philox_stream += 1
+
+    def __getstate__(self) -> dict:
+        state = dict(self.__dict__)
+        state["_graph"] = None
+        state.pop("_graph_workspaces", None)
+        if state.get("_fused") is not None:
+            state["_fused"] = None  # scratch buffers are rebuilt on the first step after loading
+        return state
+
     def _step(self):
+        if self._fused_ok():
+            if self.__dict__.get("_use_graph") and self._graph_capturable():
+                self._step_graph()
+            else:
+                self._graph = None
+                if self.__dict__.get("_fused") is not None and self._fused.get("steps_dev") is not None:
+                    self._fused["steps_dev"], self._problem.philox_stream_offset = None, None
+                self._step_fused()
+            return
         zs, ys, xs = self.sample_distribution()
         assigned_weights = self.get_population_weights(xs)
         local_m_displacement, shaped_m_displacement = self.update_m(zs, ys, assigned_weights)

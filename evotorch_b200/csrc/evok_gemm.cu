@@ -9,13 +9,20 @@
 // would break the 1e-5 parity bar of the searchers' state.
 //
 // Structure (one CTA per 128 x 256 output tile, optional split-K over blockIdx.z):
-//   warp 0      TMA producer: 4 tile loads per K-block (A_hi, A_lo, B_hi, B_lo; 128-byte swizzle), 2-stage mbarrier ring
+//   warp 0      TMA producer, 2-stage mbarrier ring.  CONVERT = true (operands 16-byte aligned, the normal case): TWO raw fp32
+//               tile loads per K-block (A, B; 128-byte swizzle) -- the tensor core ignores the 13 low mantissa bits of a tf32
+//               operand, so the raw tile IS the hi operand, and two converter warps derive the lo tiles (x - trunc(x), same
+//               swizzled positions, element-wise) in shared memory while earlier MMAs run: the operands are read from HBM exactly
+//               once and no split copies exist.  CONVERT = false (unaligned operands): 4 loads of tiles pre-split by a pre-pass
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue (12 MMAs of 128 x 256 x 8 per K-block),
 //               tcgen05.commit releases the stage / signals the epilogue
-//   warps 2-9   epilogue: the K loop is accumulated in TMEM in chunks of 4 K-blocks (two ping-pong accumulators); each finished
+//   warps 2-3   converters (CONVERT only, see warp 0)
+//   warps 4-11  epilogue: the K loop is accumulated in TMEM in chunks of 4 K-blocks (two ping-pong accumulators); each finished
 //               chunk is folded into per-thread fp32 REGISTER accumulators (round-to-nearest) via tcgen05.ld, the final tile is
 //               written through a shared-memory transpose; optional second output C2 = alpha * acc + bias[col]
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "evok_common.cuh"
 
@@ -25,7 +32,7 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 32;  // floats = 128 bytes = one swizzle span
 constexpr int kGemmStages = 2;
-constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kGemmThreads = 384;  // TMA warp, MMA warp, 2 converter warps, 8 epilogue warps (two aligned warpgroups: warp % 4 = TMEM lane quadrant)
 constexpr int kUmmaK = 8;  // tf32: 32 bytes of K per MMA
 constexpr uint32_t kTileABytes = kGemmBM * kGemmBK * 4;  // 16 KB
 constexpr uint32_t kTileBBytes = kGemmBN * kGemmBK * 4;  // 32 KB
@@ -115,6 +122,12 @@ struct GemmParams {
   int64_t ldc2;
   const float* alpha_dev;
   const float* bias;
+  // optional in-place style update  C = k[0] * acc + k[1] * E[i][j] + k[2] * u[i] * u[j]   (k: 3 device floats; CMA-ES covariance
+  // update cmaes.py:519-553 with acc = Y^T diag(w) Y, E = old C, u = p_c).  Applied by the epilogue, or by the split-K reduction.
+  const float* affine_k;
+  const float* affine_E;
+  int64_t lde;
+  const float* affine_u;
 };
 
 // The tensor core adds every MMA into the TMEM accumulator with round-toward-zero; over hundreds of MMAs that is a
@@ -123,6 +136,7 @@ struct GemmParams {
 // register accumulators with ordinary round-to-nearest fp32 adds while the MMA warp fills the other TMEM accumulator.
 constexpr int kGemmChunk = 4;
 
+template <bool CONVERT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
@@ -133,7 +147,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* empty = full + kGemmStages;
   uint64_t* tmem_full = empty + kGemmStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* conv = tmem_empty + 2;            // [kGemmStages] lo tiles of the stage derived (CONVERT)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + kGemmStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
@@ -147,6 +162,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int s = 0; s < kGemmStages; ++s) {
       bar_init(&full[s], 1);
       bar_init(&empty[s], 1);
+      bar_init(&conv[s], 2);  // one arrival per converter warp
     }
     for (int t = 0; t < 2; ++t) {
       bar_init(&tmem_full[t], 1);
@@ -167,12 +183,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const uint32_t use = i / kGemmStages;
         bar_wait(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
         unsigned char* st = base + (size_t)s * kStageBytes;
-        bar_expect_tx(&full[s], kStageBytes);
+        bar_expect_tx(&full[s], CONVERT ? kTileABytes + kTileBBytes : kStageBytes);
         const int kx = (kb_begin + i) * kGemmBK;
         tma_load_2d(st, &map_a_hi, kx, m0, &full[s]);
-        tma_load_2d(st + kTileABytes, &map_a_lo, kx, m0, &full[s]);
+        if (!CONVERT) tma_load_2d(st + kTileABytes, &map_a_lo, kx, m0, &full[s]);
         tma_load_2d(st + 2 * kTileABytes, &map_b_hi, kx, n0, &full[s]);
-        tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
+        if (!CONVERT) tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           bar_wait(&tmem_empty[buf], ((ch >> 1) - 1) & 1);
           tc_fence_after();
         }
-        bar_wait(&full[s], use & 1);
+        bar_wait(CONVERT ? &conv[s] : &full[s], use & 1);  // CONVERT: the converter warps have derived the lo tiles of this stage
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * kGemmBN);
         const uint32_t st = s32(base + (size_t)s * kStageBytes);
@@ -204,16 +220,47 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) umma_commit(&tmem_full[buf]);  // chunk accumulator complete
       }
     }
+  } else if (warp < 4) {
+    // ===== 2 converter warps (CONVERT): per K-block wait for the raw tiles, derive lo = x - trunc_tf32(x) for both operands
+    // (element-wise, so every element simply keeps its swizzled position: 3072 float4 per stage, 48 per thread), publish them to
+    // the tensor core (async proxy) and signal the MMA warp.  Runs one or two K-blocks ahead of the MMAs.
+    if (CONVERT) {
+      const int ct = threadIdx.x - 64;  // 0 .. 63
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kGemmStages;
+        const uint32_t use = i / kGemmStages;
+        bar_wait(&full[s], use & 1);
+        unsigned char* st = base + (size_t)s * kStageBytes;
+        const float4* a_raw = reinterpret_cast<const float4*>(st);
+        float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
+        const float4* b_raw = reinterpret_cast<const float4*>(st + 2 * kTileABytes);
+        float4* b_lo = reinterpret_cast<float4*>(st + 2 * kTileABytes + kTileBBytes);
+        auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+#pragma unroll 4
+        for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
+          const float4 v = a_raw[ct + 64 * j];
+          a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+        }
+#pragma unroll 4
+        for (int j = 0; j < (int)(kTileBBytes / 16 / 64); ++j) {
+          const float4 v = b_raw[ct + 64 * j];
+          b_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv[s])) : "memory");
+      }
+    }
   } else {
-    // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4 =====
     // Every thread keeps its row's 128 partial sums in REGISTERS and folds each finished TMEM chunk into them with
     // round-to-nearest fp32 adds (no memory traffic); the final tile goes out through a padded shared-memory transpose so that a
     // warp writes 4 rows x 128 contiguous bytes per instruction.
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int quad = warp & 3, half = (warp - 4) >> 2;
     float acc[kGemmBN / 2];
 #pragma unroll
     for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
-    for (int ch = 0; ch < num_chunks; ++ch) {
+    auto fold_chunk = [&](int ch) {
       const int buf = ch & 1;
       bar_wait(&tmem_full[buf], (ch >> 1) & 1);
       tc_fence_after();
@@ -227,10 +274,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
-    }
+    };
+    for (int ch = 0; ch < num_chunks; ++ch) fold_chunk(ch);
     // all MMAs have completed (the last tmem_full has fired), so the pipeline stages are free: use them as transpose scratch
-    float* stile = reinterpret_cast<float*>(base) + (size_t)(warp - 2) * (32 * kEpiPitch);
+    float* stile = reinterpret_cast<float*>(base) + (size_t)(warp - 4) * (32 * kEpiPitch);
     const float alpha = (p.C2 && p.alpha_dev) ? *p.alpha_dev : 1.0f;
+    const bool affine = p.affine_k != nullptr && gridDim.z == 1;
+    const float k0 = affine ? p.affine_k[0] : 1.0f, k1 = affine ? p.affine_k[1] : 0.0f, k2 = affine ? p.affine_k[2] : 0.0f;
     float* cbase = p.C + (int64_t)blockIdx.z * p.split_stride;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0) && (p.ldc % 4 == 0);
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
@@ -248,8 +298,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const float4 v = *reinterpret_cast<const float4*>(stile + rr * kEpiPitch + sub_col);
         if (row < p.M) {
           float* cp = cbase + (int64_t)row * p.ldc + col;
-          const float e[4] = {v.x, v.y, v.z, v.w};
-          if (vec_ok && col + 4 <= p.N) {
+          float e[4] = {v.x, v.y, v.z, v.w};
+          if (affine) {
+            const float ur = p.affine_u ? __ldg(p.affine_u + row) : 0.0f;
+            for (int t = 0; t < 4; ++t)
+              if (col + t < p.N)
+                e[t] = fmaf(k0, e[t], fmaf(k1, p.affine_E ? p.affine_E[(int64_t)row * p.lde + col + t] : 0.0f,
+                                          k2 * ur * (p.affine_u ? __ldg(p.affine_u + col + t) : 0.0f)));
+          }
+          if (!affine && vec_ok && col + 4 <= p.N) {
             *reinterpret_cast<float4*>(cp) = v;
           } else {
             for (int t = 0; t < 4; ++t)
@@ -303,13 +360,44 @@ __global__ void __launch_bounds__(256) transpose_scale_kernel(const float* __res
 }
 
 __global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ partial, int splits, int64_t split_stride, int64_t M,
-                                                            int64_t N, int64_t ldp, float* __restrict__ C, int64_t ldc) {
+                                                            int64_t N, int64_t ldp, float* C, int64_t ldc, const float* __restrict__ affine_k,
+                                                            const float* affine_E, int64_t lde, const float* __restrict__ affine_u) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   const int64_t r = i / N, c = i % N;
   float acc = 0.0f;
   for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * split_stride + r * ldp + c];
+  if (affine_k) {  // same update as the epilogue's (GemmParams::affine_*); E may alias C (element read before it is written)
+    const float e = affine_E ? affine_E[r * lde + c] : 0.0f;
+    const float uu = affine_u ? affine_u[r] * affine_u[c] : 0.0f;
+    acc = fmaf(affine_k[0], acc, fmaf(affine_k[1], e, affine_k[2] * uu));
+  }
   C[r * ldc + c] = acc;
+}
+
+// Operands of the weighted SYRK  S = Y^T diag(w) Y  as K-major matrices (K = the population axis), built in ONE pass over Y:
+//   out_w[c, r] = w[r] * Y[r, c]      out_p[c, r] = Y[r, c]          (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) transpose_pair_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int64_t cols,
+                                                             const float* __restrict__ w, float* __restrict__ out_w, float* __restrict__ out_p,
+                                                             int64_t ldo) {
+  __shared__ float tile[32][33];
+  __shared__ float wrow[32];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (ty == 0) wrow[tx] = (r0 + tx < rows) ? w[r0 + tx] : 0.0f;
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? in[r * ldi + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t c = c0 + k, r = r0 + tx;
+    if (c < cols && r < rows) {
+      const float v = tile[tx][k];
+      out_p[c * ldo + r] = v;
+      out_w[c * ldo + r] = v * wrow[tx];
+    }
+  }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -377,30 +465,53 @@ extern "C" EVOK_API size_t evok_gemm_workspace_bytes(int64_t M, int64_t N, int64
   return plan_gemm(M, N, K).total + 1024;
 }
 
-extern "C" EVOK_API int evok_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C,
-                                     int64_t ldc, float* C2, int64_t ldc2, const float* alpha_dev, const float* bias, void* ws, size_t ws_bytes,
-                                     void* stream) {
+struct GemmAffine {
+  const float* k;
+  const float* E;
+  int64_t lde;
+  const float* u;
+};
+
+static bool tma_ok(const float* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 4 == 0; }
+
+static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc, float* C2,
+                     int64_t ldc2, const float* alpha_dev, const float* bias, const GemmAffine* aff, void* ws, size_t ws_bytes, void* stream) {
   if (!A || !B || !C || !ws) return EVOK_E_NULLPTR;
   if (M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N || (C2 && ldc2 < N)) return EVOK_E_BADSIZE;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return EVOK_E_BADSIZE;
+  if (aff && (!aff->k || (aff->u && M != N) || (aff->E && aff->lde < N))) return EVOK_E_BADSIZE;
   const GemmPlan g = plan_gemm(M, N, K, C2 == nullptr);  // the fused second output needs the whole K range in one CTA
   char* w8 = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   if (ws_bytes < g.total + (size_t)(w8 - (char*)ws)) return EVOK_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  float* a_hi = (float*)(w8 + g.off_a_hi);
-  float* a_lo = (float*)(w8 + g.off_a_lo);
-  float* b_hi = (float*)(w8 + g.off_b_hi);
-  float* b_lo = (float*)(w8 + g.off_b_lo);
   float* partial = (float*)(w8 + g.off_partial);
-  split_tf32_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, g.ldk);
-  split_tf32_kernel<<<(unsigned)((N * K + 255) / 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, g.ldk);
-  EVOK_CHECK_LAUNCH_N(2);
+  // Operands that TMA can address directly (16-byte aligned base and pitch: every matrix this package allocates) are read from
+  // HBM once, by the GEMM itself, which derives the lo halves in shared memory; otherwise a pre-pass writes aligned split copies.
+  static const int allow_convert = [] {
+    const char* e = getenv("EVOK_GEMM_CONVERT");
+    return e ? atoi(e) : 1;
+  }();
+  const bool convert = allow_convert && tma_ok(A, lda) && tma_ok(B, ldb);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a_hi, M, K, g.ldk, kGemmBM))) return rc;
-  if ((rc = make_map(&ma_lo, a_lo, M, K, g.ldk, kGemmBM))) return rc;
-  if ((rc = make_map(&mb_hi, b_hi, N, K, g.ldk, kGemmBN))) return rc;
-  if ((rc = make_map(&mb_lo, b_lo, N, K, g.ldk, kGemmBN))) return rc;
+  if (convert) {
+    if ((rc = make_map(&ma_hi, A, M, K, lda, kGemmBM))) return rc;
+    if ((rc = make_map(&mb_hi, B, N, K, ldb, kGemmBN))) return rc;
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  } else {
+    float* a_hi = (float*)(w8 + g.off_a_hi);
+    float* a_lo = (float*)(w8 + g.off_a_lo);
+    float* b_hi = (float*)(w8 + g.off_b_hi);
+    float* b_lo = (float*)(w8 + g.off_b_lo);
+    split_tf32_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, g.ldk);
+    split_tf32_kernel<<<(unsigned)((N * K + 255) / 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, g.ldk);
+    EVOK_CHECK_LAUNCH_N(2);
+    if ((rc = make_map(&ma_hi, a_hi, M, K, g.ldk, kGemmBM))) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, g.ldk, kGemmBM))) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, g.ldk, kGemmBN))) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, K, g.ldk, kGemmBN))) return rc;
+  }
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.kblocks_per_split = g.kblocks_per_split;
@@ -412,19 +523,50 @@ extern "C" EVOK_API int evok_gemm_nt(const float* A, int64_t lda, const float* B
   p.ldc2 = ldc2;
   p.alpha_dev = alpha_dev;
   p.bias = bias;
+  p.affine_k = (aff && !split) ? aff->k : nullptr;
+  p.affine_E = aff ? aff->E : nullptr;
+  p.lde = aff ? aff->lde : 0;
+  p.affine_u = aff ? aff->u : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
       return (int)cudaGetLastError();
     attr_set = true;
   }
   dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((N + kGemmBN - 1) / kGemmBN), (unsigned)g.splits);
-  gemm_tf32x3_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if (convert) gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   EVOK_CHECK_LAUNCH();
   if (split) {
-    reduce_splits_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(partial, g.splits, M * N, M, N, N, C, ldc);
+    reduce_splits_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(partial, g.splits, M * N, M, N, N, C, ldc, aff ? aff->k : nullptr,
+                                                                          aff ? aff->E : nullptr, aff ? aff->lde : 0, aff ? aff->u : nullptr);
     EVOK_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" EVOK_API int evok_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C,
+                                     int64_t ldc, float* C2, int64_t ldc2, const float* alpha_dev, const float* bias, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  return gemm_impl(A, lda, B, ldb, M, N, K, C, ldc, C2, ldc2, alpha_dev, bias, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" EVOK_API int evok_gemm_nt_affine(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C,
+                                            int64_t ldc, const float* k_dev, const float* E, int64_t lde, const float* u, void* ws, size_t ws_bytes,
+                                            void* stream) {
+  if (!k_dev) return EVOK_E_NULLPTR;
+  const GemmAffine aff{k_dev, E, lde, u};
+  return gemm_impl(A, lda, B, ldb, M, N, K, C, ldc, nullptr, 0, nullptr, nullptr, &aff, ws, ws_bytes, stream);
+}
+
+extern "C" EVOK_API int evok_transpose_pair(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out_w, float* out_p,
+                                            int64_t ldo, void* stream) {
+  if (!in || !w || !out_w || !out_p) return EVOK_E_NULLPTR;
+  if (rows <= 0 || cols <= 0 || ldi < cols || ldo < rows) return EVOK_E_BADSIZE;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  transpose_pair_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, rows, cols, w, out_w, out_p, ldo);
+  EVOK_CHECK_LAUNCH();
   return 0;
 }
 

@@ -245,6 +245,13 @@ __global__ void __launch_bounds__(256) scatter_utilities_kernel(const uint32_t* 
   if (perm) perm[p] = (int64_t)i;
 }
 
+// out[solution at sorted position p] = table[p]   (CMA-ES: weight of a solution = weights[its rank], cmaes.py:445-451)
+__global__ void __launch_bounds__(256) scatter_table_kernel(const uint32_t* __restrict__ idx, int64_t N, const float* __restrict__ table,
+                                                            float* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < N) out[idx[p]] = table[p];
+}
+
 __global__ void __launch_bounds__(256) write_perm_kernel(const uint32_t* __restrict__ idx, int64_t N, int64_t* __restrict__ perm) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p < N) perm[p] = (int64_t)idx[p];
@@ -307,12 +314,12 @@ constexpr int kSmallRankMax = 8192;
 constexpr int kSmallThreads = 256;
 constexpr int kSmallTile = 2048;
 
-enum { kSmallUtilities = 0, kSmallArgsort = 1, kSmallEliteMask = 2 };
+enum { kSmallUtilities = 0, kSmallArgsort = 1, kSmallEliteMask = 2, kSmallTable = 3 };
 
 template <int PARTS>
 __global__ void __launch_bounds__(kSmallThreads)
     rank_small_kernel(const float* __restrict__ f, int N, int descending, int mode, int method, int64_t num_elites, float* __restrict__ out,
-                      int64_t* __restrict__ perm) {
+                      int64_t* __restrict__ perm, const float* __restrict__ table = nullptr) {
   __shared__ uint32_t tile[kSmallTile];
   __shared__ double red[33];
   constexpr int kElems = kSmallThreads / PARTS;
@@ -370,17 +377,20 @@ __global__ void __launch_bounds__(kSmallThreads)
     out[i] = u;
   } else if (mode == kSmallEliteMask) {
     out[i] = (int64_t)p < num_elites ? 1.0f : 0.0f;
+  } else if (mode == kSmallTable) {
+    out[i] = table[p];
   }
 }
 
-static int rank_small(const float* f, int64_t N, int descending, int mode, int method, int64_t num_elites, float* out, int64_t* perm, cudaStream_t st) {
+static int rank_small(const float* f, int64_t N, int descending, int mode, int method, int64_t num_elites, float* out, int64_t* perm, cudaStream_t st,
+                      const float* table = nullptr) {
   // lanes per element grow with N: the work per thread stays <= 512 comparisons and the grid >= N / 64 CTAs
   if (N <= 1024) {
-    rank_small_kernel<4><<<(unsigned)((N + 63) / 64), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+    rank_small_kernel<4><<<(unsigned)((N + 63) / 64), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   } else if (N <= 4096) {
-    rank_small_kernel<8><<<(unsigned)((N + 31) / 32), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+    rank_small_kernel<8><<<(unsigned)((N + 31) / 32), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   } else {
-    rank_small_kernel<16><<<(unsigned)((N + 15) / 16), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm);
+    rank_small_kernel<16><<<(unsigned)((N + 15) / 16), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   }
   EVOK_CHECK_LAUNCH();
   return 0;
@@ -708,6 +718,23 @@ extern "C" EVOK_API int evok_rank_sharded(int method, const float* f_local, int6
                                                static_cast<const double*>(peer_fsum_host[rank]),
                                                static_cast<const unsigned long long*>(peer_flags_host[rank]),
                                                reinterpret_cast<unsigned long long*>(epoch_dev), done_dev + 2, err_dev, timeout_ns, w_local, mean_out);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_rank_table(const float* keys, int64_t N, int descending, const float* table, float* out, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  if (!keys || !table || !out || !ws) return EVOK_E_NULLPTR;
+  if (N < 0 || N >= (int64_t)1 << 32) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  const SortPlan p = make_plan(N);
+  if (ws_bytes < p.total) return EVOK_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_small_rank(N)) return rank_small(keys, N, descending, kSmallTable, 0, 0, out, nullptr, st, table);
+  uint32_t* sidx = nullptr;
+  int rc = sort_pairs(keys, N, descending, ws, p, st, &sidx);
+  if (rc) return rc;
+  scatter_table_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sidx, N, table, out);
   EVOK_CHECK_LAUNCH();
   return 0;
 }

@@ -220,6 +220,48 @@ def argsort(keys: torch.Tensor, descending: bool) -> torch.Tensor:
     return perm
 
 
+def rank_table(keys: torch.Tensor, descending: bool, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = table[position of keys[i] in the stable sorted order] (position 0 = largest key if `descending`)."""
+    keys = _vec(keys, "keys")
+    n = keys.numel()
+    _vec(table, "table", n)
+    out = torch.empty_like(keys) if out is None else _vec(out, "out", n)
+    ws = _rank_ws(keys.device, n)
+    with _timed("rank"):
+        rc = nat.lib().evok_rank_table(keys.data_ptr(), n, int(bool(descending)), table.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       nat.stream_of(keys))
+    nat.check(rc, "evok_rank_table")
+    return out
+
+
+def cmaes_row_weights(assigned: torch.Tensor, Z: torch.Tensor, active: bool, w_pos: torch.Tensor, w_act: torch.Tensor) -> None:
+    """w_pos = max(assigned, 0); w_act = assigned > 0 ? assigned : D * assigned / ||z_i||^2 (or `assigned` when not `active`)."""
+    _mat(Z, "Z")
+    n, d = Z.shape
+    _vec(assigned, "assigned", n); _vec(w_pos, "w_pos", n); _vec(w_act, "w_act", n)
+    nat.check(nat.lib().evok_cmaes_row_weights(assigned.data_ptr(), Z.data_ptr(), Z.stride(0), n, d, int(bool(active)), w_pos.data_ptr(),
+                                               w_act.data_ptr(), nat.stream_of(Z)), "evok_cmaes_row_weights")
+
+
+def cmaes_vector_update(local_disp: torch.Tensor, shaped_disp: torch.Tensor, m: torch.Tensor, p_sigma: torch.Tensor, p_c: torch.Tensor,
+                        sigma: torch.Tensor, consts, csa_squared: bool, k_out: torch.Tensor, *, steps: int = 0,
+                        steps_dev: Optional[torch.Tensor] = None, h_sig_out: Optional[torch.Tensor] = None) -> None:
+    """In place: m, p_sigma, sigma (1-element tensor), p_c; k_out (3 floats) = coefficients of the covariance update."""
+    import ctypes
+
+    d = m.numel()
+    _vec(local_disp, "local_disp", d); _vec(shaped_disp, "shaped_disp", d); _vec(m, "m"); _vec(p_sigma, "p_sigma", d); _vec(p_c, "p_c", d)
+    _vec(k_out, "k_out", 3)
+    if not (sigma.is_cuda and sigma.dtype == torch.float32 and sigma.numel() == 1):
+        raise ValueError("sigma: expected a 1-element float32 CUDA tensor")
+    if steps_dev is not None and not (steps_dev.is_cuda and steps_dev.dtype == torch.int64 and steps_dev.numel() == 1):
+        raise ValueError("steps_dev: expected a 1-element int64 CUDA tensor")
+    carr = (ctypes.c_float * 10)(*[float(x) for x in consts])
+    nat.check(nat.lib().evok_cmaes_vector_update(local_disp.data_ptr(), shaped_disp.data_ptr(), d, m.data_ptr(), p_sigma.data_ptr(), p_c.data_ptr(),
+                                                 sigma.data_ptr(), nat.ptr(steps_dev), int(steps), carr, int(bool(csa_squared)), k_out.data_ptr(),
+                                                 nat.ptr(h_sig_out), nat.stream_of(m)), "evok_cmaes_vector_update")
+
+
 def weights_adjust_(w: torch.Tensor, mode: int) -> torch.Tensor:
     _vec(w, "weights")
     nat.check(nat.lib().evok_weights_adjust(w.data_ptr(), w.numel(), mode, nat.stream_of(w)), "evok_weights_adjust")
@@ -410,6 +452,33 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None
                                     0 if out2 is None else out2.stride(0), nat.ptr(alpha), nat.ptr(bias), ws.data_ptr(), ws.numel(),
                                     nat.stream_of(A))
     nat.check(rc, "evok_gemm_nt")
+    return out
+
+
+def weighted_syrk_update(Y: torch.Tensor, w: torch.Tensor, k: torch.Tensor, C: torch.Tensor, u: Optional[torch.Tensor] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = k[0] * (Y^T diag(w) Y) + k[1] * C + k[2] * u u^T  -- the rank-mu + rank-1 covariance update of CMA-ES (cmaes.py:519-553)
+    as one transposing pass over Y and one tensor-core GEMM whose epilogue (or split-K reduction) applies the update.
+    `k`: 3 device floats.  `out` may be `C` (in place)."""
+    _mat(Y, "Y"); _mat(C, "C")
+    n, d = Y.shape
+    _vec(w, "w", n); _vec(k, "k", 3)
+    if C.shape != (d, d):
+        raise ValueError(f"C: expected shape {(d, d)}, got {tuple(C.shape)}")
+    if u is not None:
+        _vec(u, "u", d)
+    out = torch.empty_like(C) if out is None else _mat(out, "out")
+    ldo = (n + 3) // 4 * 4
+    lib = nat.lib()
+    tws = nat.workspace(Y.device, 2 * d * ldo * 4 + 256, "syrk_operands")
+    base = (tws.data_ptr() + 255) // 256 * 256
+    a_w, a_p = base, base + d * ldo * 4
+    nat.check(lib.evok_transpose_pair(Y.data_ptr(), Y.stride(0), n, d, w.data_ptr(), a_w, a_p, ldo, nat.stream_of(Y)), "evok_transpose_pair")
+    ws = nat.workspace(Y.device, lib.evok_gemm_workspace_bytes(d, d, n), "gemm")
+    with _timed("gemm"):
+        rc = lib.evok_gemm_nt_affine(a_w, ldo, a_p, ldo, d, d, n, out.data_ptr(), out.stride(0), k.data_ptr(), C.data_ptr(), C.stride(0), nat.ptr(u),
+                                     ws.data_ptr(), ws.numel(), nat.stream_of(Y))
+    nat.check(rc, "evok_gemm_nt_affine")
     return out
 
 

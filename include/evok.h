@@ -110,6 +110,11 @@ int evok_rank(int method, const float* f, int64_t N, int higher_is_better, float
 int evok_argsort(const float* keys, int64_t N, int descending, int64_t* perm, void* ws, size_t ws_bytes,
                  void* stream);
 
+/* out[i] = table[position of keys[i] in the stable sorted order] -- "the weight of a solution is weights[its rank]"
+ * (CMA-ES get_population_weights, cmaes.py:445-451: argsort, inverse-permutation scatter and gather, in one call).
+ * descending != 0: position 0 is the largest key.  Same workspace as evok_rank. */
+int evok_rank_table(const float* keys, int64_t N, int descending, const float* table, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* In-place weight post-processing on the N-vector (distributions.py:562-563, :722-723 `w - mean(w)`;
  * :784-785 `w / sum|w|`).  mode 1: subtract mean; mode 2: divide by sum of absolute values. */
 int evok_weights_adjust(float* w, int64_t N, int mode, void* stream);
@@ -212,8 +217,33 @@ int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, in
 size_t evok_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int evok_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                  float* C2, int64_t ldc2, const float* alpha_dev, const float* bias, void* ws, size_t ws_bytes, void* stream);
+/* The same product with a fused affine update of the output (no second pass over C):
+ *   C[i][j] = k[0] * (A B^T)[i][j] + k[1] * E[i][j] + k[2] * u[i] * u[j]        k_dev: 3 device floats; E, u nullable (u needs M == N)
+ * E may be C itself.  Replaces the covariance update of CMA-ES, cmaes.py:519-553:
+ *   C <- C + c1a (pc pc^T - C) + c_mu (Y^T diag(w) Y - sum(w) C)   with k = (c_mu, 1 - c1a - c_mu sum(w), c1a * weighted_pc^2), u = p_c. */
+int evok_gemm_nt_affine(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                        const float* k_dev, const float* E, int64_t lde, const float* u, void* ws, size_t ws_bytes, void* stream);
 /* out[c, r] = (w ? w[r] : 1) * in[r, c]: builds the K-major operands of the weighted SYRK */
 int evok_transpose_scale(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out, int64_t ldo, void* stream);
+/* both SYRK operands in one pass over `in`:  out_w[c, r] = w[r] * in[r, c],  out_p[c, r] = in[r, c] */
+int evok_transpose_pair(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out_w, float* out_p, int64_t ldo,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CMA-ES generation glue (algorithms/cmaes.py): the vector arithmetic between the dense contractions, fused.
+ *   evok_cmaes_row_weights  : w_positive[i] = max(a_i, 0) (recombination weights, cmaes.py:468-475) and the active-CMA reweighting
+ *       w_active[i] = a_i > 0 ? a_i : D * a_i / ||z_i||^2 (cmaes.py:531-535; active == 0: w_active = a).  One pass over Z.
+ *   evok_cmaes_vector_update: one single-CTA kernel for update_m / update_p_sigma / update_sigma / _h_sig / update_p_c
+ *       (cmaes.py:454-517, :31-46), all in place; k_out[0..2] = (c_mu, 1 - c1a - c_mu * sum(w), c1a * weighted_pc^2) are the
+ *       coefficients of the covariance update for evok_gemm_nt_affine.  consts_host: 10 host floats
+ *       (c_m, c_sigma, damp_sigma, c_c, c_1, c_mu, variance_discount_sigma, variance_discount_c, unbiased_expectation, sum(weights)).
+ *       The generation counter of _h_sig comes from *steps_dev (then incremented by the kernel: CUDA-graph replay) or steps_host.
+ * --------------------------------------------------------------------------------------------- */
+int evok_cmaes_row_weights(const float* assigned_weights, const float* Z, int64_t ldz, int64_t N, int64_t D, int active, float* w_positive,
+                           float* w_active, void* stream);
+int evok_cmaes_vector_update(const float* local_disp, const float* shaped_disp, int64_t D, float* m, float* p_sigma, float* p_c, float* sigma_dev,
+                             int64_t* steps_dev, int64_t steps_host, const float* consts_host, int csa_squared, float* k_out, float* h_sig_out,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Peer exchange over NVLink / NVSwitch: the two collectives of the sharded generation (the reference's Ray round trip,

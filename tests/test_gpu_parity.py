@@ -364,3 +364,69 @@ def test_sharded_ranking_is_bit_identical_to_the_global_sort(method, hib, counts
     assert all(torch.equal(mean[0], m) for m in mean)
     close(float(mean[0]), float(f2.double().mean()), rtol=1e-6)
     del finite
+
+
+# ------------------------------------------------------------------------------------------------ CMA-ES fused generation
+def _cma(seed=5, D=96, n=384, graph=False, fused=True, **kw):
+    prob = Problem("min", sphere, initial_bounds=(-3, 3), solution_length=D, device=DEV, seed=seed)
+    c = CMAES(prob, stdev_init=1.0, popsize=n, **kw)
+    if not fused:
+        c._fused_ok = lambda: False  # the op-by-op mirror of the reference's _step
+    if graph:
+        c.enable_cuda_graph()
+    return c
+
+
+@pytest.mark.parametrize("kw", [{}, {"active": False}, {"csa_squared": True}, {"limit_C_decomposition": False}])
+def test_cmaes_fused_generation_equals_the_op_by_op_path(kw):
+    """The fused generation (rank-to-weights, row weights, one vector-update kernel, covariance update in the SYRK epilogue)
+    against the op-by-op mirror of the reference's `_step` (cmaes.py:567-606), same Philox draws: m, sigma, C, A, paths."""
+    a, b = _cma(fused=True, **kw), _cma(fused=False, **kw)
+    for g in range(6):
+        a.step(); b.step()
+        close(N(a.m), N(b.m), rtol=2e-5, atol=2e-6)
+        close(float(a.sigma), float(b.sigma), rtol=2e-5)
+        close(N(a.p_sigma), N(b.p_sigma), rtol=2e-5, atol=2e-5)
+        close(N(a.p_c), N(b.p_c), rtol=2e-5, atol=2e-5)
+        close(N(a.C), N(b.C), rtol=2e-5, atol=2e-6)
+        close(N(a.A), N(b.A), rtol=5e-5, atol=5e-6)
+
+
+def test_cmaes_cuda_graph_replay_equals_eager_stepping():
+    """`enable_cuda_graph()`: the whole generation (cuSOLVER Cholesky included) replayed from one graph launch must give the
+    same bits as eager fused stepping (device-side Philox generation counter and step counter)."""
+    a, b = _cma(D=128, n=512, limit_C_decomposition=False), _cma(D=128, n=512, limit_C_decomposition=False, graph=True)
+    for g in range(8):
+        a.step(); b.step()
+    if b._graph is None:
+        pytest.skip("the generation could not be captured on this build (library call not capturable)")
+    assert torch.equal(a.m, b.m) and torch.equal(a.C, b.C) and torch.equal(a.A, b.A) and torch.equal(a.p_sigma, b.p_sigma)
+    assert float(a.sigma) == float(b.sigma) and a.status["mean_eval"] == b.status["mean_eval"]
+    assert b.status["iter"] == 8
+
+
+def test_rank_table_and_affine_syrk_kernels():
+    """evok_rank_table == weights[rank] by argsort / scatter / gather (cmaes.py:445-451) bit for bit; evok_gemm_nt_affine ==
+    k0 Y^T diag(w) Y + k1 C + k2 u u^T in float64 (direct epilogue and split-K reduction, in place)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for n in (12, 4096, 20000):
+        f = torch.round(torch.randn(n, device=DEV, generator=g) * 100) / 100
+        table = torch.randn(n, device=DEV, generator=g)
+        for desc in (False, True):
+            idx = torch.argsort(f, descending=desc, stable=True)
+            ranks = torch.empty_like(idx)
+            ranks[idx] = torch.arange(n, device=DEV)
+            assert torch.equal(ops.rank_table(f, desc, table), table[ranks])
+    for n, d in ((12, 6), (4096, 1024), (300, 130), (5000, 256)):
+        Y = torch.randn(n, d, device=DEV, generator=g)
+        w = torch.randn(n, device=DEV, generator=g) / n
+        Cm = torch.randn(d, d, device=DEV, generator=g)
+        u = torch.randn(d, device=DEV, generator=g)
+        k = torch.tensor([0.7, 0.9, 0.05], device=DEV)
+        ref = 0.7 * (Y.double().T * w.double()) @ Y.double() + 0.9 * Cm.double() + 0.05 * torch.outer(u.double(), u.double())
+        out = ops.weighted_syrk_update(Y, w, k, Cm, u=u)
+        scale = float(ref.abs().max())
+        assert float((out.double() - ref).abs().max()) / scale < 3e-6
+        C2 = Cm.clone()
+        ops.weighted_syrk_update(Y, w, k, C2, u=u, out=C2)  # in place
+        assert torch.equal(C2, out)
