@@ -413,6 +413,7 @@ class Problem(Clonable):
         return obj_index % n
 
     # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
     def evaluate(self, x: Union["SolutionBatch", "Solution"]):
         """Evaluate a batch in place (core.py:2532-2571): hooks, `_evaluate_batch`, best/worst bookkeeping."""
         if isinstance(x, Solution):

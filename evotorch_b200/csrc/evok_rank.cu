@@ -2,6 +2,8 @@
 // (4 passes x 8 bits; per pass: per-tile digit histogram -> per-digit exclusive scan -> stable scatter using
 // warp match/ballot ranking), followed by a fused utility-table scatter.  N is the population size
 // (<= a few million): the whole working set lives in L2, the kernels are latency-, not bandwidth-bound.
+#include <cstdlib>
+
 #include "evok_common.cuh"
 
 namespace evok {
@@ -47,18 +49,17 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts[(int64_t)d * n_tiles + blockIdx.x] = h[d];
 }
 
-// Fused variant for few tiles (sharded ranking: N / world keys per GPU): the histogram kernel's LAST CTA also performs the
-// per-digit exclusive scan over the tiles (thread d owns digit d: n_tiles <= kFusedScanMaxTiles sequential adds), which
-// removes the digit_scan launch of every pass; with FIRST the kernel also builds the orderable keys / indices from the
-// fitnesses, which removes make_keys.  `done` is a zero-initialised counter that returns to zero.
-constexpr int kFusedScanMaxTiles = 256;
+// Variant for moderate tile counts (n_tiles <= kSelfScanMaxTiles, i.e. up to 512 k keys -- every sharded ranking and most
+// populations): the histogram kernel writes its counts TILE-major (counts_t[tile][digit]) and, on the first pass, also builds
+// the orderable keys / indices from the fitnesses; the scatter kernel then derives its own offsets (thread d sums digit d over
+// the tiles: n_tiles coalesced, independent loads), so a pass is 2 launches instead of 3 and make_keys disappears.
+constexpr int kSelfScanMaxTiles = 256;
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads)
-    radix_hist_scan_kernel(const float* __restrict__ f, int descending, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, int64_t N, int shift,
-                           uint32_t* __restrict__ counts, int n_tiles, uint32_t* __restrict__ totals, unsigned int* done) {
+    radix_hist_t_kernel(const float* __restrict__ f, int descending, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, int64_t N, int shift,
+                        uint32_t* __restrict__ counts_t) {
   __shared__ uint32_t h[kRadix];
-  __shared__ bool last;
   for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * kTile;
@@ -79,24 +80,7 @@ __global__ void __launch_bounds__(kSortThreads)
     }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts[(int64_t)d * n_tiles + blockIdx.x] = h[d];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  {  // kSortThreads == kRadix: thread d scans digit d over the tiles
-    uint32_t* row = counts + (int64_t)threadIdx.x * n_tiles;
-    uint32_t run = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const uint32_t c = __ldcg(row + t);
-      row[t] = run;
-      run += c;
-    }
-    totals[threadIdx.x] = run;
-  }
-  if (threadIdx.x == 0) *done = 0;
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) counts_t[(int64_t)blockIdx.x * kRadix + d] = h[d];
 }
 
 // per digit d (one CTA each): exclusive scan in place of counts[d][0..n_tiles) and the digit total.
@@ -141,6 +125,8 @@ __global__ void __launch_bounds__(256) digit_scan_kernel(uint32_t* __restrict__ 
 
 // stable scatter of one tile.  Item order inside a tile: warp w owns the contiguous range
 // [w*256, (w+1)*256); iteration `it` covers 32 consecutive items, lane = position.
+// SELF_SCAN: `offsets` holds tile-major raw counts (radix_hist_t_kernel); thread d sums digit d over the tiles itself
+template <bool SELF_SCAN>
 __global__ void __launch_bounds__(kSortThreads)
     radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ keys_out,
                          uint32_t* __restrict__ idx_out, int64_t N, int shift, const uint32_t* __restrict__ offsets, int n_tiles,
@@ -148,10 +134,23 @@ __global__ void __launch_bounds__(kSortThreads)
   __shared__ uint32_t wcount[kSortWarps][kRadix];  // per-warp digit counts, then per-warp exclusive bases
   __shared__ uint32_t digit_base[kRadix];          // exclusive scan of the digit totals
   __shared__ uint32_t wtot[kSortWarps];
+  __shared__ uint32_t tile_prefix[kRadix];         // SELF_SCAN: keys of digit d in the tiles before this one
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&wcount[0][0])[i] = 0;
   {  // kSortThreads == kRadix: thread d owns digit d
-    const uint32_t t = totals[threadIdx.x];
+    uint32_t t;
+    if (SELF_SCAN) {
+      uint32_t before = 0, all = 0;
+      for (int tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t c = offsets[(int64_t)tile * kRadix + threadIdx.x];
+        all += c;
+        before += tile < (int)blockIdx.x ? c : 0u;
+      }
+      tile_prefix[threadIdx.x] = before;
+      t = all;
+    } else {
+      t = totals[threadIdx.x];
+    }
     uint32_t incl = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(kSortThreads)
   __syncthreads();
   // per digit: exclusive scan over the warps (in warp order) + global tile offset
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
-    uint32_t run = digit_base[d] + offsets[(int64_t)d * n_tiles + blockIdx.x];
+    uint32_t run = digit_base[d] + (SELF_SCAN ? tile_prefix[d] : offsets[(int64_t)d * n_tiles + blockIdx.x]);
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       const uint32_t c = wcount[w][d];
@@ -430,22 +429,26 @@ static SortPlan make_plan(int64_t N) {
 }
 
 // sorts; returns the device pointer (inside ws) of the sorted index array (and of the sorted keys).
-// `fused_done` (nullable): a zero-initialised device counter; with it and few enough tiles the 13-launch pipeline shrinks to 8
-// (histogram + scan fused, keys made by the first histogram).
+// Up to kSelfScanMaxTiles tiles (512 k keys) the 13-launch pipeline (make_keys + 4 x (hist, scan, scatter)) shrinks to 8
+// (4 x (hist [+ keys], self-scanning scatter)); EVOK_RANK_SELF_SCAN=0 forces the 3-kernel passes.
 static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const SortPlan& p, cudaStream_t st, uint32_t** sorted_idx,
-                      uint32_t** sorted_keys = nullptr, unsigned int* fused_done = nullptr) {
+                      uint32_t** sorted_keys = nullptr) {
   char* base = (char*)ws;
   uint32_t* keys[2] = {(uint32_t*)(base + p.off_keys0), (uint32_t*)(base + p.off_keys1)};
   uint32_t* idx[2] = {(uint32_t*)(base + p.off_idx0), (uint32_t*)(base + p.off_idx1)};
   uint32_t* counts = (uint32_t*)(base + p.off_counts);
   uint32_t* totals = (uint32_t*)(base + p.off_totals);
-  if (fused_done && p.n_tiles <= kFusedScanMaxTiles) {
+  static const int self_scan = [] {
+    const char* e = getenv("EVOK_RANK_SELF_SCAN");
+    return e ? atoi(e) : 1;
+  }();
+  if (self_scan && p.n_tiles <= kSelfScanMaxTiles) {
     int cur = 0;
     for (int pass = 0; pass < 32 / kRadixBits; ++pass) {
       const int shift = pass * kRadixBits;
-      if (pass == 0) radix_hist_scan_kernel<true><<<p.n_tiles, kSortThreads, 0, st>>>(f, descending, keys[0], idx[0], N, shift, counts, p.n_tiles, totals, fused_done);
-      else radix_hist_scan_kernel<false><<<p.n_tiles, kSortThreads, 0, st>>>(nullptr, 0, keys[cur], nullptr, N, shift, counts, p.n_tiles, totals, fused_done);
-      radix_scatter_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
+      if (pass == 0) radix_hist_t_kernel<true><<<p.n_tiles, kSortThreads, 0, st>>>(f, descending, keys[0], idx[0], N, shift, counts);
+      else radix_hist_t_kernel<false><<<p.n_tiles, kSortThreads, 0, st>>>(nullptr, 0, keys[cur], nullptr, N, shift, counts);
+      radix_scatter_kernel<true><<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
       EVOK_CHECK_LAUNCH_N(2);
       cur ^= 1;
     }
@@ -460,7 +463,7 @@ static int sort_pairs(const float* f, int64_t N, int descending, void* ws, const
     const int shift = pass * kRadixBits;
     radix_hist_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], N, shift, counts, p.n_tiles);
     digit_scan_kernel<<<kRadix, 256, 0, st>>>(counts, p.n_tiles, totals);
-    radix_scatter_kernel<<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
+    radix_scatter_kernel<false><<<p.n_tiles, kSortThreads, 0, st>>>(keys[cur], idx[cur], keys[cur ^ 1], idx[cur ^ 1], N, shift, counts, p.n_tiles, totals);
     EVOK_CHECK_LAUNCH_N(3);
     cur ^= 1;
   }
@@ -700,7 +703,7 @@ extern "C" EVOK_API int evok_rank_sharded(int method, const float* f_local, int6
   const unsigned long long* epoch = reinterpret_cast<const unsigned long long*>(epoch_dev);
   uint32_t *sidx = nullptr, *skeys = nullptr;
   if (n_local > 0) {
-    int rc = sort_pairs(f_local, n_local, !higher_is_better, ws, p, st, &sidx, &skeys, done_dev + 0);
+    int rc = sort_pairs(f_local, n_local, !higher_is_better, ws, p, st, &sidx, &skeys);
     if (rc) return rc;
   }
   int push_grid = (int)((n_local + 255) / 256);

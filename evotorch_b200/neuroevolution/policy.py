@@ -117,6 +117,20 @@ class Policy:
         return functional_call(self._net, self._unflatten(flat), (x,))
 
     @torch.no_grad()
+    def forward_shared(self, parameters: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """Row i of `parameters` (N x L) applied to the SAME input batch `x` (B x in) -> N x B x out: a population scored on a
+        common minibatch (supervisedne.py:337-347).  For feed-forward nets on CUDA float32 the layers run on the kernels of
+        `ops.mlp_forward_shared` (first layer: one tensor-core product of the stacked weight rows of all N networks with the
+        shared batch); anything else goes through `vmap(functional_call)`."""
+        if parameters.ndim != 2 or parameters.shape[1] != self.parameter_length:
+            raise ValueError(f"Expected parameters of shape (N, {self.parameter_length}), got {tuple(parameters.shape)}")
+        if (self._spec is not None and ops.uses_kernels(parameters) and ops.uses_kernels(x) and x.ndim == 2 and parameters.stride(1) == 1
+                and hasattr(ops, "mlp_forward_shared")):
+            dims, acts = self._spec
+            return ops.mlp_forward_shared(parameters, x, dims, acts)
+        return vmap(self._call_one, in_dims=(0, None))(parameters, x)
+
+    @torch.no_grad()
     def __call__(self, x: torch.Tensor, *, obs_norm=None, active: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Row i of the parameters applied to observation i (vecrl.py:1240-1279).  Rollout extras, fused into the K8 kernel
         on CUDA float32: `obs_norm` (a RunningNorm) normalises and clips the observations on the fly, `active` (bool, N)

@@ -7,6 +7,8 @@ from . import cloning, hook, misc, ranking, readonlytensor
 from .cloning import Clonable, Serializable, deep_clone
 from .hook import Hook
 from .misc import (
+    device_of,
+    dtype_of,
     clip_tensor,
     clone,
     empty_tensor_like,

@@ -360,3 +360,21 @@ def clone(x: Any, *, memo: Optional[dict] = None) -> Any:
     from .cloning import deep_clone
 
     return deep_clone(x, otherwise_deepcopy=True, memo={} if memo is None else memo)
+
+
+def device_of(x: Any) -> torch.device:
+    """Device of a tensor, of a module (its first parameter) or of any object with a `device` attribute (tools/misc.py:2014-2037)."""
+    if isinstance(x, torch.nn.Module):
+        for param in x.parameters():
+            return param.device
+        raise ValueError(f"Cannot determine the device of the module {x}")
+    return x.device
+
+
+def dtype_of(x: Any):
+    """dtype of a tensor / array, of a module (its first parameter) or of any object with a `dtype` attribute (tools/misc.py:2040-2063)."""
+    if isinstance(x, torch.nn.Module):
+        for param in x.parameters():
+            return param.dtype
+        raise ValueError(f"Cannot determine the dtype of the module {x}")
+    return x.dtype
