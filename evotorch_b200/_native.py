@@ -28,6 +28,15 @@ _SIGNATURES = {
     "evok_rank_workspace_bytes": (c_size_t, [c_int64]),
     "evok_rank": (c_int, [c_int, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
     "evok_argsort": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "evok_sample_batched": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint64, _P]),
+    "evok_rank_batched": (c_int, [c_int, _P, c_int64, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "evok_elite_mask_batched": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "evok_weights_adjust_batched": (c_int, [_P, c_int64, c_int64, c_int, _P]),
+    "evok_grad_batched_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "evok_grad_batched": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_float, c_float, _P, _P, _P,
+                                  c_size_t, _P]),
+    "evok_clipup_batched": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "evok_sigma_update_batched": (c_int, [_P, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P]),
     "evok_rank_table": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
     "evok_cmaes_row_weights": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "evok_cmaes_vector_update": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, c_int, _P, _P, _P]),

@@ -7,6 +7,8 @@ then clamped against the old stdev (SURVEY 8 rows a6 + a8; kernels K3, K4 in its
 
 from __future__ import annotations
 
+import os
+
 from typing import NamedTuple
 
 import torch
@@ -68,6 +70,21 @@ def cem_tell(state: CEMState, values: torch.Tensor, evals: torch.Tensor) -> CEMS
     new_mus, new_sigmas = new_center.view(-1, d), new_stdev.view(-1, d)
     kernels = on_kernels(center, values)
     sense = "max" if state.maximize else "min"
+    if kernels and os.environ.get("EVOTORCH_B200_FUNCTIONAL_LOOP", "0") != "1":  # (=1: the per-item launch chains, for comparison)
+        # one launch per stage for ALL batch items: raw utilities, elite flags, elite moments, mean / std of the elites, clamped update
+        import math
+
+        n = xs.shape[1]
+        num_elites = math.floor(n * state.parenthood_ratio)
+        w = ops.rank_batched(fs, "raw", state.maximize)
+        mask = ops.elite_mask_batched(w, num_elites)
+        s1, s2 = ops.grad_batched(ops.GRAD_MOMENTS, xs, mask, mus if center.ndim > 1 else center, sigmas if state.stdev.ndim > 1 else state.stdev,
+                                  1.0, 1.0)
+        B = s1.shape[0]
+        gmu, gsig = ops.cem_finalize(s1.view(-1), s2.view(-1), new_sigmas.reshape(-1), num_elites)
+        ops.axpy_(new_mus.view(-1), gmu, 1.0)
+        ops.sigma_update_batched_(new_sigmas, gsig.view(B, d), [1.0] * B, False, lb=lbs.contiguous(), ub=ubs.contiguous(), max_change=mcs.contiguous())
+        return state._replace(center=new_center, stdev=new_stdev)
     for b in range(mus.shape[0]):
         dist = SeparableGaussian({"mu": mus[b].contiguous(), "sigma": sigmas[b].contiguous(), "parenthood_ratio": state.parenthood_ratio})
         grads = dist.compute_gradients(xs[b], fs[b], objective_sense=sense)  # mean(elites) - mu, std(elites) - sigma

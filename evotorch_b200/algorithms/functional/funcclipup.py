@@ -2,7 +2,7 @@
 
     velocity <- momentum * velocity + lr * g / ||g||;   if ||velocity|| > max_speed: velocity <- max_speed * velocity / ||velocity||
     center   <- center + velocity
-On CUDA float32 each batch item is one launch of the K5 `evok_clipup_step` kernel writing the NEW state tensors.
+On CUDA float32 all batch items are ONE launch of the K5 `evok_clipup_batched` kernel (a CTA per item) writing the NEW state tensors.
 """
 
 from __future__ import annotations
@@ -57,8 +57,8 @@ def clipup_tell(state: ClipUpState, *, follow_grad) -> ClipUpState:
         new_velocity = expand_to(state.velocity, batch, 1).contiguous().clone()
         gs = flat_items(g, batch, 1).contiguous()
         cs, vs = new_center.view(-1, center.shape[-1]), new_velocity.view(-1, center.shape[-1])
-        for b, (lr_b, mom_b, cap_b) in enumerate(zip(scalar_items(lr, batch), scalar_items(mom, batch), scalar_items(cap, batch))):
-            ops.clipup_step(gs[b], vs[b], lr_b, mom_b, cap_b, mu=cs[b])
+        # ONE launch for all batch items (one CTA per item; the per-item hyper-parameters travel in the launch parameters)
+        ops.clipup_batched_(gs, vs, cs, scalar_items(lr, batch), scalar_items(mom, batch), scalar_items(cap, batch))
     else:
         dev = center.device
         lr_, mom_, cap_ = (x.to(dev)[..., None] for x in (lr, mom, cap))

@@ -7,6 +7,8 @@ reductions K4 and the ClipUp / Adam / SGD + clamped-sigma updates K5 -- here dri
 
 from __future__ import annotations
 
+import os
+
 from typing import NamedTuple, Optional, Union
 
 import torch
@@ -77,10 +79,10 @@ def sample_separable(center: torch.Tensor, stdev: torch.Tensor, popsize: int, sy
     out = torch.empty(tuple(batch) + (popsize, d), dtype=center.dtype, device=center.device)
     mus, sigmas, outs = flat_items(center, batch, 1), flat_items(stdev, batch, 1), out.view(-1, popsize, d)
     if on_kernels(center, stdev):
-        seed = draw_philox_seed()
-        for b in range(outs.shape[0]):  # K1; the batch index is the Philox stream, so the items are independent draws of one key
-            ops.sample_eval(ops.OBJ_NONE, outs[b], mus[b].contiguous(), sigmas[b].contiguous(), n_rows=popsize, symmetric=symmetric, seed=seed,
-                            stream_id=b)
+        # K1, ONE launch for all batch items (grid y = item); the batch index is the Philox stream, so the items are independent
+        # draws of one key
+        ops.sample_batched(outs, mus if center.ndim > 1 else center, sigmas if stdev.ndim > 1 else stdev, symmetric=symmetric,
+                           seed=draw_philox_seed())
     else:
         for b in range(outs.shape[0]):
             _distribution(symmetric, mus[b], sigmas[b]).sample(out=outs[b])
@@ -112,6 +114,19 @@ def pgpe_tell(state: PGPEState, values: torch.Tensor, evals: torch.Tensor) -> PG
     new_stdev = expand_to(state.stdev, batch, 1).contiguous().clone()
     new_sigmas = new_stdev.view(-1, d)
     kernels = on_kernels(center, values)
+    if kernels and os.environ.get("EVOTORCH_B200_FUNCTIONAL_LOOP", "0") != "1":  # (=1: the per-item launch chains, for comparison)
+        # one launch per stage for ALL batch items (grid y / z = item): K3 ranking, K4 weighted reductions, K5 sigma update
+        n = xs.shape[1]
+        w = ops.rank_batched(fs, state.ranking_method, state.maximize)
+        if state.ranking_method not in ("centered", "normalized"):  # distributions.py:562-563 / :722-723: w - mean(w)
+            ops.weights_adjust_batched_(w, 1)
+        scale = 1.0 / (n // 2) if state.symmetric else 1.0 / n  # divide by num_directions / num_solutions (funcpgpe.py defaults)
+        form = ops.GRAD_SYMMETRIC if state.symmetric else ops.GRAD_SEPARABLE
+        gmu, gsig = ops.grad_batched(form, xs, w, mus if center.ndim > 1 else center, sigmas if state.stdev.ndim > 1 else state.stdev, scale, scale)
+        ops.sigma_update_batched_(new_sigmas, gsig, scalar_items(lr_sigma, batch), False, lb=lbs.contiguous(), ub=ubs.contiguous(),
+                                  max_change=mcs.contiguous())
+        new_optimizer_state = tell(state.optimizer_state, follow_grad=gmu.view(tuple(batch) + (d,)))
+        return state._replace(optimizer_state=new_optimizer_state, stdev=new_stdev)
     for b, lr_b in enumerate(scalar_items(lr_sigma, batch)):
         dist = _distribution(state.symmetric, mus[b].contiguous(), sigmas[b].contiguous())
         grads = dist.compute_gradients(xs[b], fs[b], objective_sense=sense, ranking_method=state.ranking_method)  # K3 + K4

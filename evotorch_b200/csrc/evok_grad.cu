@@ -50,13 +50,27 @@ __device__ __forceinline__ VecF<VEC> load_row(const float* p) {
   return r;
 }
 
+// Batched searches (functional API): blockIdx.z = batch item; element strides between the items' operands (0 = shared)
+struct GradItems {
+  int64_t x, w, mu, sigma, partial;
+};
+
 // SYM: unit r = direction (rows 2r, 2r+1), else unit r = row r.  REGEN: eps = sigma * z regenerated from Philox.
 template <int VEC, int TX, bool SYM, bool REGEN>
 __global__ void __launch_bounds__(kGradThreads, EVOK_GRAD_MINB)
     grad_partial_kernel(int form, const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, const float* __restrict__ mu,
                         const float* __restrict__ sigma, int64_t n_units, int64_t D, int64_t units_per_chunk, uint64_t unit0,
-                        const __grid_constant__ PhiloxKey key, const uint32_t* __restrict__ stream_off, float* __restrict__ partial) {
+                        const __grid_constant__ PhiloxKey key, const uint32_t* __restrict__ stream_off, float* __restrict__ partial,
+                        const __grid_constant__ GradItems items) {
   constexpr int TY = kGradThreads / TX;
+  if (gridDim.z > 1) {
+    const int64_t item = blockIdx.z;
+    X += item * items.x;
+    w += item * items.w;
+    mu += item * items.mu;
+    sigma += item * items.sigma;
+    partial += item * items.partial;
+  }
   const uint32_t sw = key.stream_lo + ((REGEN && stream_off) ? __ldg(stream_off) : 0u);
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int64_t col = ((int64_t)blockIdx.x * TX + tx) * VEC;
@@ -173,9 +187,13 @@ __global__ void __launch_bounds__(kGradThreads, EVOK_GRAD_MINB)
 }
 
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restrict__ partial, int n_chunks, int64_t D, float scale_mu,
-                                                            float scale_sigma, float* __restrict__ out_mu, float* __restrict__ out_sigma) {
+                                                            float scale_sigma, float* __restrict__ out_mu, float* __restrict__ out_sigma,
+                                                            int64_t item_stride_partial = 0) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= D) return;
+  partial += (int64_t)blockIdx.y * item_stride_partial;  // batched: blockIdx.y = item, outputs contiguous [items][D]
+  out_mu += (int64_t)blockIdx.y * D;
+  out_sigma += (int64_t)blockIdx.y * D;
   float t1 = 0.0f, t2 = 0.0f;
   for (int c = 0; c < n_chunks; ++c) {
     t1 += partial[((int64_t)c * 2 + 0) * D + j];
@@ -418,12 +436,13 @@ static GradPlan plan_grad(int64_t n_units, int64_t D, bool vec_ok) {
 template <int VEC, bool SYM, bool REGEN>
 static void launch_partial(const GradPlan& p, int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma,
                            int64_t n_units, int64_t D, uint64_t unit0, uint64_t seed, uint64_t stream_id, const uint32_t* stream_off, float* partial,
-                           cudaStream_t st) {
-  dim3 grid(p.n_coltiles, p.n_chunks);
+                           cudaStream_t st, int64_t n_items = 1, const GradItems* items = nullptr) {
+  dim3 grid(p.n_coltiles, p.n_chunks, (unsigned)n_items);
   const PhiloxKey key = make_philox_key(seed, stream_id);
+  const GradItems it = items ? *items : GradItems{0, 0, 0, 0, 0};
 #define EVOK_LAUNCH_TX(TXV)                                                                                                         \
   grad_partial_kernel<VEC, TXV, SYM, REGEN><<<grid, kGradThreads, 0, st>>>(form, X, ldx, w, mu, sigma, n_units, D, p.units_per_chunk, \
-                                                                           unit0, key, stream_off, partial)
+                                                                           unit0, key, stream_off, partial, it)
   switch (p.tx) {
     case 32: EVOK_LAUNCH_TX(32); break;
     case 64: EVOK_LAUNCH_TX(64); break;
@@ -532,4 +551,62 @@ extern "C" EVOK_API int evok_grad_push(int form, const float* X, int64_t ldx, co
   push.done = done_dev;
   return grad_impl(form, X, X ? ldx : 0, w, mu, sigma, row0, n_rows, D, X == nullptr, seed, stream_id, stream_offset_dev, scale_mu, scale_sigma, nullptr,
                    nullptr, ws, ws_bytes, stream, &push);
+}
+
+// Batched searches: n_items independent weighted column reductions in ONE launch chain (blockIdx.z = item).  X: [items][n_rows][D]
+// (item stride item_stride_x elements), w: [items][n_rows] contiguous, mu / sigma: item strides (0 = shared by all items),
+// outputs contiguous [items][D].  Same arithmetic as evok_grad per item (LDG kernel, fixed-order two-stage reduction).
+extern "C" EVOK_API size_t evok_grad_batched_workspace_bytes(int64_t n_items, int64_t n_rows, int64_t D) {
+  if (n_items <= 0 || D <= 0) return 256;
+  (void)n_rows;
+  // all items together use about one wave of CTAs: sum over items of n_chunks * 2 * D <= (592 / coltiles) * 2 * D + (2 per item of slack) * 2 * D
+  return ((size_t)kMaxResidentCtas * 1024 + 4 * (size_t)n_items * (size_t)D + 64) * sizeof(float);
+}
+
+extern "C" EVOK_API int evok_grad_batched(int form, const float* X, int64_t item_stride_x, int64_t ldx, const float* w, const float* mu,
+                                          int64_t item_stride_mu, const float* sigma, int64_t item_stride_sigma, int64_t n_items, int64_t n_rows,
+                                          int64_t D, float scale_mu, float scale_sigma, float* out_mu, float* out_sigma, void* ws, size_t ws_bytes,
+                                          void* stream) {
+  if (!X || !w || !mu || !sigma || !out_mu || !out_sigma || !ws) return EVOK_E_NULLPTR;
+  if (form < EVOK_GRAD_SEPARABLE || form > EVOK_GRAD_MOMENTS) return EVOK_E_BADENUM;
+  if (n_items < 0 || n_items > 65535 || n_rows < 0 || D <= 0 || ldx < D) return EVOK_E_BADSIZE;
+  const bool sym = form == EVOK_GRAD_SYMMETRIC;
+  if (sym && (n_rows & 1)) return EVOK_E_ODDROWS;
+  if (n_items == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_units = sym ? n_rows / 2 : n_rows;
+  if (n_units == 0) {
+    cudaMemsetAsync(out_mu, 0, (size_t)n_items * D * 4, st);
+    cudaMemsetAsync(out_sigma, 0, (size_t)n_items * D * 4, st);
+    return 0;
+  }
+  const bool vec_ok = (D % 4 == 0) && (ldx % 4 == 0) && aligned16(X) && item_stride_x % 4 == 0 && item_stride_mu % 4 == 0 && item_stride_sigma % 4 == 0;
+  GradPlan p = plan_grad(n_units, D, vec_ok);
+  // the batch fills the GPU: fewer row chunks per item keep the fixed-order finalisation short
+  int64_t chunks = ((int64_t)kNumSMs * EVOK_GRAD_CTAS_PER_SM + (int64_t)p.n_coltiles * n_items - 1) / ((int64_t)p.n_coltiles * n_items);
+  if (chunks < p.n_chunks) {
+    if (chunks < 1) chunks = 1;
+    p.units_per_chunk = (n_units + chunks - 1) / chunks;
+    p.n_chunks = (int)((n_units + p.units_per_chunk - 1) / p.units_per_chunk);
+  }
+  GradItems items;
+  items.x = item_stride_x;
+  items.w = n_rows;
+  items.mu = item_stride_mu;
+  items.sigma = item_stride_sigma;
+  items.partial = (int64_t)p.n_chunks * 2 * D;
+  if (ws_bytes < (size_t)n_items * items.partial * sizeof(float)) return EVOK_E_WORKSPACE;
+  float* partial = (float*)ws;
+  if (vec_ok) {
+    if (sym) launch_partial<4, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, 0, 0, 0, nullptr, partial, st, n_items, &items);
+    else launch_partial<4, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, 0, 0, 0, nullptr, partial, st, n_items, &items);
+  } else {
+    if (sym) launch_partial<1, true, false>(p, form, X, ldx, w, mu, sigma, n_units, D, 0, 0, 0, nullptr, partial, st, n_items, &items);
+    else launch_partial<1, false, false>(p, form, X, ldx, w, mu, sigma, n_units, D, 0, 0, 0, nullptr, partial, st, n_items, &items);
+  }
+  EVOK_CHECK_LAUNCH();
+  grad_finalize_kernel<<<dim3((unsigned)((D + 255) / 256), (unsigned)n_items), 256, 0, st>>>(partial, p.n_chunks, D, scale_mu, scale_sigma, out_mu,
+                                                                                             out_sigma, items.partial);
+  EVOK_CHECK_LAUNCH();
+  return 0;
 }

@@ -259,6 +259,8 @@ __global__ void __launch_bounds__(256) write_perm_kernel(const uint32_t* __restr
 // normalized / raw: no sort.  stats[0] = mean, stats[1] = unbiased std of g = +-f (double accumulation).
 __global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict__ f, int64_t N, float sign, float* __restrict__ stats) {
   __shared__ double sm[33];
+  f += (int64_t)blockIdx.x * N;  // batched: one CTA per item, stats[2 * item ..]
+  stats += 2 * blockIdx.x;
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < N; i += 1024) s += (double)(sign * f[i]);
   const double mean = block_sum<double>(s, sm) / (double)N;
@@ -277,6 +279,9 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ f
                                                      int normalized, float* __restrict__ w) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  f += (int64_t)blockIdx.y * N;  // batched: blockIdx.y = item
+  w += (int64_t)blockIdx.y * N;
+  stats += 2 * blockIdx.y;
   const float g = sign * f[i];
   w[i] = normalized ? __fdiv_rn(g - stats[0], stats[1]) : g;
 }
@@ -284,6 +289,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ f
 // in-place weight adjustments
 __global__ void __launch_bounds__(1024) weights_adjust_kernel(float* __restrict__ w, int64_t N, int mode) {
   __shared__ double sm[33];
+  w += (int64_t)blockIdx.x * N;  // batched: one CTA per item
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < N; i += 1024) s += mode == 1 ? (double)w[i] : (double)fabsf(w[i]);
   const double tot = block_sum<double>(s, sm);
@@ -322,6 +328,12 @@ __global__ void __launch_bounds__(kSmallThreads)
   __shared__ uint32_t tile[kSmallTile];
   __shared__ double red[33];
   constexpr int kElems = kSmallThreads / PARTS;
+  {  // batched searches: blockIdx.y = batch item, every item ranks its own N fitnesses (the table, if any, is shared)
+    const int64_t item_off = (int64_t)blockIdx.y * N;
+    f += item_off;
+    if (out) out += item_off;
+    if (perm) perm += item_off;
+  }
   const int part = threadIdx.x % PARTS;
   const int i = blockIdx.x * kElems + threadIdx.x / PARTS;
   uint32_t ki = 0;
@@ -382,14 +394,14 @@ __global__ void __launch_bounds__(kSmallThreads)
 }
 
 static int rank_small(const float* f, int64_t N, int descending, int mode, int method, int64_t num_elites, float* out, int64_t* perm, cudaStream_t st,
-                      const float* table = nullptr) {
+                      const float* table = nullptr, int64_t n_items = 1) {
   // lanes per element grow with N: the work per thread stays <= 512 comparisons and the grid >= N / 64 CTAs
   if (N <= 1024) {
-    rank_small_kernel<4><<<(unsigned)((N + 63) / 64), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
+    rank_small_kernel<4><<<dim3((unsigned)((N + 63) / 64), (unsigned)n_items), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   } else if (N <= 4096) {
-    rank_small_kernel<8><<<(unsigned)((N + 31) / 32), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
+    rank_small_kernel<8><<<dim3((unsigned)((N + 31) / 32), (unsigned)n_items), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   } else {
-    rank_small_kernel<16><<<(unsigned)((N + 15) / 16), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
+    rank_small_kernel<16><<<dim3((unsigned)((N + 15) / 16), (unsigned)n_items), kSmallThreads, 0, st>>>(f, (int)N, descending, mode, method, num_elites, out, perm, table);
   }
   EVOK_CHECK_LAUNCH();
   return 0;
@@ -738,6 +750,56 @@ extern "C" EVOK_API int evok_rank_table(const float* keys, int64_t N, int descen
   int rc = sort_pairs(keys, N, descending, ws, p, st, &sidx);
   if (rc) return rc;
   scatter_table_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sidx, N, table, out);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- batched searches (functional API with leading batch dimensions): n_items independent rankings of N fitnesses each, f and w
+// contiguous [n_items][N].  N <= 8192: ONE launch for all items (the counting rank with blockIdx.y = item); larger N: the radix
+// pipeline item by item on the same workspace.
+extern "C" EVOK_API int evok_rank_batched(int method, const float* f, int64_t N, int64_t n_items, int higher_is_better, float* w, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  if (!f || !w || !ws) return EVOK_E_NULLPTR;
+  if (method < EVOK_RANK_CENTERED || method > EVOK_RANK_RAW) return EVOK_E_BADENUM;
+  if (N < 0 || N >= (int64_t)1 << 32 || n_items < 0 || n_items > 65535) return EVOK_E_BADSIZE;
+  if (N == 0 || n_items == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (method == EVOK_RANK_NORMALIZED || method == EVOK_RANK_RAW) {
+    if (ws_bytes < (size_t)n_items * 8 + 256) return EVOK_E_WORKSPACE;
+    float* stats = (float*)ws;
+    const float sign = higher_is_better ? 1.0f : -1.0f;
+    if (method == EVOK_RANK_NORMALIZED) mean_std_kernel<<<(unsigned)n_items, 1024, 0, st>>>(f, N, sign, stats);
+    affine_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)n_items), 256, 0, st>>>(f, N, sign, stats, method == EVOK_RANK_NORMALIZED, w);
+    EVOK_CHECK_LAUNCH_N(method == EVOK_RANK_NORMALIZED ? 2 : 1);
+    return 0;
+  }
+  if (use_small_rank(N)) return rank_small(f, N, !higher_is_better, kSmallUtilities, method, 0, w, nullptr, st, nullptr, n_items);
+  for (int64_t b = 0; b < n_items; ++b) {
+    const int rc = evok_rank(method, f + b * N, N, higher_is_better, w + b * N, nullptr, ws, ws_bytes, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" EVOK_API int evok_elite_mask_batched(const float* w, int64_t N, int64_t n_items, int64_t num_elites, float* mask, void* ws,
+                                                size_t ws_bytes, void* stream) {
+  if (!w || !mask || !ws) return EVOK_E_NULLPTR;
+  if (N < 0 || N >= (int64_t)1 << 32 || n_items < 0 || n_items > 65535 || num_elites < 0 || num_elites > N) return EVOK_E_BADSIZE;
+  if (N == 0 || n_items == 0) return 0;
+  if (use_small_rank(N)) return rank_small(w, N, /*descending=*/1, kSmallEliteMask, 0, num_elites, mask, nullptr, (cudaStream_t)stream, nullptr, n_items);
+  for (int64_t b = 0; b < n_items; ++b) {
+    const int rc = evok_elite_mask(w + b * N, N, num_elites, mask + b * N, ws, ws_bytes, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" EVOK_API int evok_weights_adjust_batched(float* w, int64_t N, int64_t n_items, int mode, void* stream) {
+  if (!w) return EVOK_E_NULLPTR;
+  if (mode != 1 && mode != 2) return EVOK_E_BADENUM;
+  if (N < 0 || n_items < 0 || n_items > 65535) return EVOK_E_BADSIZE;
+  if (N == 0 || n_items == 0) return 0;
+  weights_adjust_kernel<<<(unsigned)n_items, 1024, 0, (cudaStream_t)stream>>>(w, N, mode);
   EVOK_CHECK_LAUNCH();
   return 0;
 }

@@ -132,6 +132,30 @@ __global__ void __launch_bounds__(kSampleThreads, SampleTune<OBJ>::kMinBlocks)
   if (PUSH) peer_signal_tail(sink, epoch, done);
 }
 
+// Batched searches (functional ask/tell API with leading batch dimensions, funcpgpe.py:301-327): blockIdx.y = batch item, every
+// item has its own centre / stdev row (item stride 0 = shared) and its own Philox stream (stream word + item), so one launch
+// draws the populations of all items -- bit-identical to one evok_sample_eval call per item with stream_id = item.
+template <bool SYM, bool VEC>
+__global__ void __launch_bounds__(kSampleThreads, SampleTune<EVOK_OBJ_NONE>::kMinBlocks)
+    sample_batched_kernel(float* __restrict__ X, int64_t item_stride_x, int64_t ldx, const float* __restrict__ mu, int64_t item_stride_mu,
+                          const float* __restrict__ sigma, int64_t item_stride_sigma, int64_t n_units, int64_t D, const __grid_constant__ PhiloxKey key) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = blockIdx.y;
+  X += item * item_stride_x;
+  mu += item * item_stride_mu;
+  sigma += item * item_stride_sigma;
+  const uint32_t sw = key.stream_lo + (uint32_t)item;
+  const int64_t warps_total = (int64_t)gridDim.x * (kSampleThreads / 32);
+  const int64_t gw = (int64_t)blockIdx.x * (kSampleThreads / 32) + (threadIdx.x >> 5);
+  const uint32_t nq = (uint32_t)((D + 3) >> 2);
+  for (int64_t u = gw; u < n_units; u += warps_total) {
+    ObjAcc<EVOK_OBJ_NONE> accp, accm;
+    float* xp = X + (SYM ? 2 * u : u) * ldx;
+    float* xm = xp + ldx;
+    for (uint32_t q = lane; q < nq; q += 32) sample_group<EVOK_OBJ_NONE, SYM, true, VEC>(key, sw, (uint64_t)u, q, D, mu, sigma, xp, xm, accp, accm);
+  }
+}
+
 constexpr int kEvalThreads = 256;
 
 template <int OBJ, bool VEC>
@@ -309,4 +333,36 @@ extern "C" EVOK_API int evok_eval(int objective, const float* X, int64_t ldx, in
     case EVOK_OBJ_ACKLEY: return launch_eval<EVOK_OBJ_ACKLEY>(X, ldx, n_rows, D, f, st);
   }
   return EVOK_E_BADENUM;
+}
+
+extern "C" EVOK_API int evok_sample_batched(float* X, int64_t item_stride_x, int64_t ldx, const float* mu, int64_t item_stride_mu, const float* sigma,
+                                            int64_t item_stride_sigma, int64_t n_items, int64_t n_rows, int64_t D, int symmetric, uint64_t seed,
+                                            uint64_t stream_id0, void* stream) {
+  if (!X || !mu || !sigma) return EVOK_E_NULLPTR;
+  if (n_items < 0 || n_items > 65535 || n_rows < 0 || D <= 0 || ldx < D || item_stride_x < 0 || item_stride_mu < 0 || item_stride_sigma < 0)
+    return EVOK_E_BADSIZE;
+  if (symmetric && (n_rows & 1)) return EVOK_E_ODDROWS;
+  if (n_items == 0 || n_rows == 0) return 0;
+  const int64_t n_units = symmetric ? n_rows / 2 : n_rows;
+  const bool vec = (D % 4 == 0) && aligned16(mu) && aligned16(sigma) && aligned16(X) && ldx % 4 == 0 && item_stride_x % 4 == 0 &&
+                   item_stride_mu % 4 == 0 && item_stride_sigma % 4 == 0;
+  int64_t ctas = (n_units + (kSampleThreads / 32) - 1) / (kSampleThreads / 32);
+  const int64_t cap = ((int64_t)sm_count() * 8 + n_items - 1) / n_items;  // about 8 CTAs per SM over all items
+  if (ctas > cap) ctas = cap < 1 ? 1 : cap;
+  const PhiloxKey key = make_philox_key(seed, stream_id0);
+  dim3 grid((unsigned)ctas, (unsigned)n_items);
+  cudaStream_t st = (cudaStream_t)stream;
+#define EVOK_LAUNCH_SB(SYMV, VECV)                                                                                                    \
+  sample_batched_kernel<SYMV, VECV><<<grid, kSampleThreads, 0, st>>>(X, item_stride_x, ldx, mu, item_stride_mu, sigma, item_stride_sigma, \
+                                                                     n_units, D, key)
+  if (symmetric) {
+    if (vec) EVOK_LAUNCH_SB(true, true);
+    else EVOK_LAUNCH_SB(true, false);
+  } else {
+    if (vec) EVOK_LAUNCH_SB(false, true);
+    else EVOK_LAUNCH_SB(false, false);
+  }
+#undef EVOK_LAUNCH_SB
+  EVOK_CHECK_LAUNCH();
+  return 0;
 }

@@ -100,6 +100,71 @@ __global__ void __launch_bounds__(256) sigma_update_kernel(float* __restrict__ s
   sigma[i] = r;
 }
 
+// Batched searches: per-item scalar hyper-parameters travel BY VALUE in the launch parameters (no device copy, no sync)
+constexpr int kItemsPerLaunch = 256;
+struct ItemScalars {
+  float a[kItemsPerLaunch], b[kItemsPerLaunch], c[kItemsPerLaunch];
+};
+
+// one CTA per item: the ClipUp step of clipup_kernel on row blockIdx.x of [items][D] tensors, with that item's (lr, momentum, max_speed)
+__global__ void __launch_bounds__(kUpdThreads) clipup_batched_kernel(const float* __restrict__ g, int64_t D, float* __restrict__ velocity,
+                                                                     float* __restrict__ center, const __grid_constant__ ItemScalars sc) {
+  __shared__ double sm[33];
+  const int item = blockIdx.x;
+  const float stepsize = sc.a[item], momentum = sc.b[item], max_speed = sc.c[item];
+  g += (int64_t)item * D;
+  velocity += (int64_t)item * D;
+  center += (int64_t)item * D;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < D; i += kUpdThreads) {
+    const double v = (double)g[i];
+    acc += v * v;
+  }
+  const float gnorm = (float)sqrt(block_sum<double>(acc, sm));
+  acc = 0.0;
+  for (int64_t i = threadIdx.x; i < D; i += kUpdThreads) {
+    const float nv = momentum * velocity[i] + __fdiv_rn(g[i], gnorm) * stepsize;
+    velocity[i] = nv;
+    acc += (double)nv * (double)nv;
+  }
+  const float vnorm = (float)sqrt(block_sum<double>(acc, sm));
+  const bool clip = vnorm > max_speed;
+  const float ratio = clip ? __fdiv_rn(max_speed, vnorm) : 1.0f;
+  for (int64_t i = threadIdx.x; i < D; i += kUpdThreads) {
+    float nv = velocity[i];
+    if (clip) {
+      nv *= ratio;
+      velocity[i] = nv;
+    }
+    center[i] += nv;
+  }
+}
+
+// sigma_update_kernel on [items][D] tensors with a per-item learning rate (blockIdx.y = item)
+__global__ void __launch_bounds__(256) sigma_update_batched_kernel(float* __restrict__ sigma, const float* __restrict__ g, int64_t D, int exp_form,
+                                                                   const float* __restrict__ lb_vec, const float* __restrict__ ub_vec,
+                                                                   const float* __restrict__ mc_vec, const __grid_constant__ ItemScalars sc) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int64_t i = (int64_t)blockIdx.y * D + j;
+  const float s = sigma[i];
+  const float step = sc.a[blockIdx.y] * g[i];
+  float target = exp_form ? s * expf(0.5f * step) : s + step;
+  float lo = lb_vec ? lb_vec[i] : -INFINITY;
+  float hi = ub_vec ? ub_vec[i] : INFINITY;
+  if (lo != lo) lo = -INFINITY;
+  if (hi != hi) hi = INFINITY;
+  const float c = mc_vec ? mc_vec[i] : NAN;
+  if (c == c) {
+    const float allowed = fabsf(s) * c;
+    lo = fmaxf(lo, s - allowed);
+    hi = fminf(hi, s + allowed);
+  }
+  float r = (target != target) ? target : fmaxf(target, lo);
+  r = (r != r) ? r : fminf(r, hi);
+  sigma[i] = r;
+}
+
 __global__ void __launch_bounds__(256) cem_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                                                            const float* __restrict__ sigma, int64_t D, float E, float* __restrict__ grad_mu,
                                                            float* __restrict__ grad_sigma) {
@@ -170,6 +235,40 @@ extern "C" EVOK_API int evok_cem_finalize(const float* s1, const float* s2, cons
   if (D <= 0 || num_elites < 1) return EVOK_E_BADSIZE;
   cem_finalize_kernel<<<nblk(D), 256, 0, (cudaStream_t)stream>>>(s1, s2, sigma, D, (float)num_elites, grad_mu, grad_sigma);
   EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_clipup_batched(const float* g, int64_t n_items, int64_t D, float* velocity, float* center, const float* stepsize_host,
+                                            const float* momentum_host, const float* max_speed_host, void* stream) {
+  if (!g || !velocity || !center || !stepsize_host || !momentum_host || !max_speed_host) return EVOK_E_NULLPTR;
+  if (D <= 0 || n_items < 0) return EVOK_E_BADSIZE;
+  for (int64_t b0 = 0; b0 < n_items; b0 += kItemsPerLaunch) {
+    const int n = (int)((n_items - b0) < kItemsPerLaunch ? (n_items - b0) : kItemsPerLaunch);
+    ItemScalars sc;
+    for (int i = 0; i < n; ++i) {
+      sc.a[i] = stepsize_host[b0 + i];
+      sc.b[i] = momentum_host[b0 + i];
+      sc.c[i] = max_speed_host[b0 + i];
+    }
+    clipup_batched_kernel<<<n, kUpdThreads, 0, (cudaStream_t)stream>>>(g + b0 * D, D, velocity + b0 * D, center + b0 * D, sc);
+    EVOK_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" EVOK_API int evok_sigma_update_batched(float* sigma, const float* g, int64_t n_items, int64_t D, const float* lr_host, int exp_form,
+                                                  const float* lb_vec, const float* ub_vec, const float* mc_vec, void* stream) {
+  if (!sigma || !g || !lr_host) return EVOK_E_NULLPTR;
+  if (D <= 0 || n_items < 0) return EVOK_E_BADSIZE;
+  for (int64_t b0 = 0; b0 < n_items; b0 += kItemsPerLaunch) {
+    const int n = (int)((n_items - b0) < kItemsPerLaunch ? (n_items - b0) : kItemsPerLaunch);
+    ItemScalars sc;
+    for (int i = 0; i < n; ++i) sc.a[i] = lr_host[b0 + i];
+    const int64_t off = b0 * D;
+    sigma_update_batched_kernel<<<dim3(nblk(D), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+        sigma + off, g + off, D, exp_form, lb_vec ? lb_vec + off : nullptr, ub_vec ? ub_vec + off : nullptr, mc_vec ? mc_vec + off : nullptr, sc);
+    EVOK_CHECK_LAUNCH();
+  }
   return 0;
 }
 

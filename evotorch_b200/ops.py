@@ -377,6 +377,124 @@ def cem_finalize(s1: torch.Tensor, s2: torch.Tensor, sigma: torch.Tensor, num_el
     return gm, gs
 
 
+# ------------------------------------------------------------------------------------------------ batched searches (functional API)
+def _items(t: torch.Tensor, core_shape: tuple, name: str) -> tuple:
+    """(tensor, n_items or None, item stride in elements) of an operand that is either shared (shape == core_shape, stride 0) or
+    contiguous [items, *core_shape]."""
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise ValueError(f"{name}: expected a float32 CUDA tensor")
+    t = as_plain_tensor(t)
+    if tuple(t.shape) == tuple(core_shape):
+        return t.contiguous(), None, 0
+    if tuple(t.shape[1:]) != tuple(core_shape) or t.ndim != len(core_shape) + 1:
+        raise ValueError(f"{name}: expected shape {core_shape} or (items, {', '.join(map(str, core_shape))}), got {tuple(t.shape)}")
+    t = t.contiguous()
+    return t, t.shape[0], int(t.stride(0))
+
+
+def sample_batched(out: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, *, symmetric: bool, seed: int, stream_id0: int = 0) -> torch.Tensor:
+    """out[b] ~ N(mu[b], diag(sigma[b]^2)) for every batch item in one launch; item b uses Philox stream stream_id0 + b."""
+    if not (out.is_cuda and out.dtype == torch.float32 and out.ndim == 3 and out.is_contiguous()):
+        raise ValueError("out: expected a contiguous float32 CUDA tensor of shape (items, popsize, D)")
+    B, n, d = out.shape
+    mu, bm, sm = _items(mu, (d,), "mu")
+    sigma, bs, ss = _items(sigma, (d,), "sigma")
+    for cnt in (bm, bs):
+        if cnt is not None and cnt != B:
+            raise ValueError("mu / sigma: number of items differs from out")
+    if symmetric and n % 2:
+        raise ValueError(f"Symmetric sampling cannot be done if the number of solutions is odd: {n}")
+    with _timed("sample"):
+        rc = nat.lib().evok_sample_batched(out.data_ptr(), n * d, d, mu.data_ptr(), sm, sigma.data_ptr(), ss, B, n, d, int(symmetric),
+                                           seed & 0xFFFFFFFFFFFFFFFF, stream_id0 & 0xFFFFFFFFFFFFFFFF, nat.stream_of(out))
+    nat.check(rc, "evok_sample_batched")
+    return out
+
+
+def rank_batched(f: torch.Tensor, method: str, higher_is_better: bool) -> torch.Tensor:
+    """Utilities of `items` independent fitness vectors, f: (items, N)."""
+    if not (f.is_cuda and f.dtype == torch.float32 and f.ndim == 2):
+        raise ValueError("f: expected a float32 CUDA tensor of shape (items, N)")
+    f = as_plain_tensor(f).contiguous()
+    B, n = f.shape
+    w = torch.empty_like(f)
+    lib = nat.lib()
+    ws = nat.workspace(f.device, max(lib.evok_rank_workspace_bytes(n), 8 * B + 256), "rank")
+    with _timed("rank"):
+        rc = lib.evok_rank_batched(RANK_IDS[method], f.data_ptr(), n, B, int(bool(higher_is_better)), w.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   nat.stream_of(f))
+    nat.check(rc, "evok_rank_batched")
+    return w
+
+
+def elite_mask_batched(w: torch.Tensor, num_elites: int) -> torch.Tensor:
+    w = as_plain_tensor(w).contiguous()
+    B, n = w.shape
+    mask = torch.empty_like(w)
+    ws = _rank_ws(w.device, n)
+    nat.check(nat.lib().evok_elite_mask_batched(w.data_ptr(), n, B, num_elites, mask.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(w)),
+              "evok_elite_mask_batched")
+    return mask
+
+
+def weights_adjust_batched_(w: torch.Tensor, mode: int) -> torch.Tensor:
+    B, n = w.shape
+    nat.check(nat.lib().evok_weights_adjust_batched(w.data_ptr(), n, B, mode, nat.stream_of(w)), "evok_weights_adjust_batched")
+    return w
+
+
+def grad_batched(form: int, X: torch.Tensor, w: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, scale_mu: float, scale_sigma: float) -> tuple:
+    """K4 for `items` independent searches in one launch chain.  X: (items, N, D), w: (items, N), mu / sigma: (D,) or (items, D)."""
+    if not (X.is_cuda and X.dtype == torch.float32 and X.ndim == 3):
+        raise ValueError("X: expected a float32 CUDA tensor of shape (items, N, D)")
+    X = as_plain_tensor(X).contiguous()
+    B, n, d = X.shape
+    w = as_plain_tensor(w).contiguous()
+    if tuple(w.shape) != (B, n):
+        raise ValueError(f"w: expected shape {(B, n)}, got {tuple(w.shape)}")
+    mu, bm, sm = _items(mu, (d,), "mu")
+    sigma, bs, ss = _items(sigma, (d,), "sigma")
+    out_mu = torch.empty(B, d, dtype=torch.float32, device=X.device)
+    out_sigma = torch.empty_like(out_mu)
+    lib = nat.lib()
+    ws = nat.workspace(X.device, lib.evok_grad_batched_workspace_bytes(B, n, d), "grad_batched")
+    with _timed("grad"):
+        rc = lib.evok_grad_batched(form, X.data_ptr(), n * d, d, w.data_ptr(), mu.data_ptr(), sm, sigma.data_ptr(), ss, B, n, d, scale_mu, scale_sigma,
+                                   out_mu.data_ptr(), out_sigma.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(X))
+    nat.check(rc, "evok_grad_batched")
+    return out_mu, out_sigma
+
+
+def _host_floats(values, n: int):
+    import ctypes
+
+    vals = [float(v) for v in values]
+    if len(vals) != n:
+        raise ValueError(f"expected {n} per-item scalars, got {len(vals)}")
+    return (ctypes.c_float * n)(*vals)
+
+
+def clipup_batched_(g: torch.Tensor, velocity: torch.Tensor, center: torch.Tensor, stepsizes, momenta, max_speeds) -> None:
+    """In place on contiguous (items, D) tensors: one CTA per item (per-item hyper-parameters are host scalars)."""
+    B, d = center.shape
+    for t, name in ((g, "g"), (velocity, "velocity"), (center, "center")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, d)):
+            raise ValueError(f"{name}: expected a contiguous float32 CUDA tensor of shape {(B, d)}")
+    nat.check(nat.lib().evok_clipup_batched(g.data_ptr(), B, d, velocity.data_ptr(), center.data_ptr(), _host_floats(stepsizes, B),
+                                            _host_floats(momenta, B), _host_floats(max_speeds, B), nat.stream_of(g)), "evok_clipup_batched")
+
+
+def sigma_update_batched_(sigma: torch.Tensor, g: torch.Tensor, lrs, exp_form: bool, lb: Optional[torch.Tensor] = None,
+                          ub: Optional[torch.Tensor] = None, max_change: Optional[torch.Tensor] = None) -> None:
+    """In place on contiguous (items, D) tensors; lb / ub / max_change: (items, D) tensors or None."""
+    B, d = sigma.shape
+    for t, name in ((sigma, "sigma"), (g, "g"), (lb, "lb"), (ub, "ub"), (max_change, "max_change")):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, d)):
+            raise ValueError(f"{name}: expected a contiguous float32 CUDA tensor of shape {(B, d)}")
+    nat.check(nat.lib().evok_sigma_update_batched(sigma.data_ptr(), g.data_ptr(), B, d, _host_floats(lrs, B), int(bool(exp_form)), nat.ptr(lb),
+                                                  nat.ptr(ub), nat.ptr(max_change), nat.stream_of(sigma)), "evok_sigma_update_batched")
+
+
 # ------------------------------------------------------------------------------------------------ K8
 ACT_IDS = {"none": 0, "identity": 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 

@@ -230,6 +230,33 @@ int evok_transpose_pair(const float* in, int64_t ldi, int64_t rows, int64_t cols
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched searches: the functional ask / tell API with leading batch dimensions (algorithms/functional/funcpgpe.py:67, :301, :330,
+ * funccem.py, funcclipup.py:95-108; `expects_ndim`, decorators.py:613).  n_items independent searches of the same shape run in ONE
+ * launch per stage (grid y / z = item) instead of one launch chain per item.  Tensors are contiguous [items][...] unless an item
+ * stride is given (stride 0 = the operand is shared by all items).  Per-item scalar hyper-parameters are HOST arrays (they travel in
+ * the launch parameters).  Every stage computes exactly what its single-search entry point computes per item.
+ * --------------------------------------------------------------------------------------------- */
+/* K1: item b draws with Philox stream (stream_id0 + b): same bits as evok_sample_eval(..., stream_id = stream_id0 + b) per item */
+int evok_sample_batched(float* X, int64_t item_stride_x, int64_t ldx, const float* mu, int64_t item_stride_mu, const float* sigma,
+                        int64_t item_stride_sigma, int64_t n_items, int64_t n_rows, int64_t D, int symmetric, uint64_t seed, uint64_t stream_id0,
+                        void* stream);
+/* K3: f, w: [items][N].  ws: max(evok_rank_workspace_bytes(N), 8 * n_items + 256) bytes */
+int evok_rank_batched(int method, const float* f, int64_t N, int64_t n_items, int higher_is_better, float* w, void* ws, size_t ws_bytes,
+                      void* stream);
+int evok_elite_mask_batched(const float* w, int64_t N, int64_t n_items, int64_t num_elites, float* mask, void* ws, size_t ws_bytes, void* stream);
+int evok_weights_adjust_batched(float* w, int64_t N, int64_t n_items, int mode, void* stream);
+/* K4: X [items][n_rows][D] (item stride / row pitch given), w [items][n_rows], out_mu / out_sigma [items][D] */
+size_t evok_grad_batched_workspace_bytes(int64_t n_items, int64_t n_rows, int64_t D);
+int evok_grad_batched(int form, const float* X, int64_t item_stride_x, int64_t ldx, const float* w, const float* mu, int64_t item_stride_mu,
+                      const float* sigma, int64_t item_stride_sigma, int64_t n_items, int64_t n_rows, int64_t D, float scale_mu, float scale_sigma,
+                      float* out_mu, float* out_sigma, void* ws, size_t ws_bytes, void* stream);
+/* K5: g, velocity, center [items][D]; center += step.  sigma, g, lb / ub / mc vectors (nullable) [items][D] */
+int evok_clipup_batched(const float* g, int64_t n_items, int64_t D, float* velocity, float* center, const float* stepsize_host,
+                        const float* momentum_host, const float* max_speed_host, void* stream);
+int evok_sigma_update_batched(float* sigma, const float* g, int64_t n_items, int64_t D, const float* lr_host, int exp_form, const float* lb_vec,
+                              const float* ub_vec, const float* mc_vec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * CMA-ES generation glue (algorithms/cmaes.py): the vector arithmetic between the dense contractions, fused.
  *   evok_cmaes_row_weights  : w_positive[i] = max(a_i, 0) (recombination weights, cmaes.py:468-475) and the active-CMA reweighting
  *       w_active[i] = a_i > 0 ? a_i : D * a_i / ||z_i||^2 (cmaes.py:531-535; active == 0: w_active = a).  One pass over Z.

@@ -7,7 +7,7 @@ sys.path.insert(0, ".")
 from evotorch_b200 import ops  # noqa: E402
 
 dev = "cuda"
-for n in (32, 1000, 4096, 8192, 8193, 20000, 100000, 1000000):
+for n in (32, 1000, 4096, 8192, 8193, 20000, 100000, 125000, 250000, 500000, 1000000):
     f = torch.randn(n, device=dev)
     w = torch.empty(n, device=dev)
     for _ in range(5):

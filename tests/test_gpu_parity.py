@@ -430,3 +430,93 @@ def test_rank_table_and_affine_syrk_kernels():
         C2 = Cm.clone()
         ops.weighted_syrk_update(Y, w, k, C2, u=u, out=C2)  # in place
         assert torch.equal(C2, out)
+
+
+# ------------------------------------------------------------------------------------------------ batched functional kernels
+@pytest.mark.parametrize("shape", [(5, 40, 12), (3, 1000, 100), (2, 20000, 64), (1, 30, 7)])
+def test_batched_stage_kernels_equal_the_per_item_kernels(shape):
+    """every batched stage (grid y / z = batch item) computes exactly what its single-search entry point computes per
+    item: K1 bit-identical, K3 bit-identical, K4 / K5 to fp32 summation order."""
+    B, n, d = shape
+    g = torch.Generator(device=DEV).manual_seed(B * n + d)
+    mu = torch.randn(B, d, device=DEV, generator=g)
+    sg = torch.rand(B, d, device=DEV, generator=g) + 0.5
+    for sym in (True, False):
+        X = torch.empty(B, n, d, device=DEV)
+        ops.sample_batched(X, mu, sg, symmetric=sym, seed=77, stream_id0=3)
+        for b in range(B):
+            ref = torch.empty(n, d, device=DEV)
+            ops.sample_eval(ops.OBJ_NONE, ref, mu[b].contiguous(), sg[b].contiguous(), n_rows=n, symmetric=sym, seed=77, stream_id=3 + b)
+            assert torch.equal(X[b], ref)
+        Xs = torch.empty(B, n, d, device=DEV)
+        ops.sample_batched(Xs, mu[0].contiguous(), sg[0].contiguous(), symmetric=sym, seed=77)  # shared centre / stdev
+        ref = torch.empty(n, d, device=DEV)
+        ops.sample_eval(ops.OBJ_NONE, ref, mu[0].contiguous(), sg[0].contiguous(), n_rows=n, symmetric=sym, seed=77, stream_id=B - 1)
+        assert torch.equal(Xs[B - 1], ref)
+    f = torch.round(torch.randn(B, n, device=DEV, generator=g) * 20) / 20
+    for method in METHODS_ALL:
+        for hib in (False, True):
+            w = ops.rank_batched(f, method, hib)
+            for b in range(B):
+                assert torch.equal(w[b], ops.rank(f[b].contiguous(), method, hib)), (method, hib, b)
+    wm = ops.rank_batched(f, "raw", True)
+    mask = ops.elite_mask_batched(wm, max(1, n // 4))
+    for b in range(B):
+        assert torch.equal(mask[b], ops.elite_mask(wm[b].contiguous(), max(1, n // 4)))
+    w = ops.rank_batched(f, "nes", False)
+    w2 = w.clone()
+    ops.weights_adjust_batched_(w2, 1)
+    for b in range(B):
+        assert torch.equal(w2[b], ops.weights_adjust_(w[b].clone(), 1))
+    for form in (ops.GRAD_SYMMETRIC, ops.GRAD_SEPARABLE, ops.GRAD_EXP, ops.GRAD_MOMENTS):
+        gm, gs = ops.grad_batched(form, X, w, mu, sg, 0.5, 2.0)
+        for b in range(B):
+            rm, rs = ops.grad(form, X[b], w[b].contiguous(), mu[b].contiguous(), sg[b].contiguous(), 0.5, 2.0)
+            close(N(gm[b]), N(rm), rtol=1e-4, atol=1e-6 * float(rm.abs().max()) + 1e-9)
+            close(N(gs[b]), N(rs), rtol=1e-4, atol=1e-6 * float(rs.abs().max()) + 1e-9)
+    gm, gs = ops.grad_batched(ops.GRAD_SEPARABLE, X, w, mu[0].contiguous(), sg[0].contiguous(), 1.0, 1.0)  # shared centre / stdev
+    rm, rs = ops.grad(ops.GRAD_SEPARABLE, X[B - 1], w[B - 1].contiguous(), mu[0].contiguous(), sg[0].contiguous(), 1.0, 1.0)
+    close(N(gm[B - 1]), N(rm), rtol=1e-4, atol=1e-6 * float(rm.abs().max()) + 1e-9)
+    # K5
+    grad = torch.randn(B, d, device=DEV, generator=g)
+    vel, cen = torch.randn(B, d, device=DEV, generator=g) * 0.1, mu.clone()
+    v2, c2 = vel.clone(), cen.clone()
+    lrs, moms, caps = [0.1 + 0.01 * b for b in range(B)], [0.9 - 0.05 * b for b in range(B)], [0.15 + 0.02 * b for b in range(B)]
+    ops.clipup_batched_(grad, vel, cen, lrs, moms, caps)
+    for b in range(B):
+        vb, cb = v2[b].clone(), c2[b].clone()
+        ops.clipup_step(grad[b].contiguous(), vb, lrs[b], moms[b], caps[b], mu=cb)
+        assert torch.equal(vb, vel[b]) and torch.equal(cb, cen[b])
+    s1, lb, ub, mc = sg.clone(), torch.full_like(sg, 0.3), torch.full_like(sg, 1.2), torch.full_like(sg, 0.2)
+    s2 = s1.clone()
+    ops.sigma_update_batched_(s1, grad, lrs, False, lb=lb, ub=ub, max_change=mc)
+    for b in range(B):
+        sb = s2[b].clone()
+        ops.sigma_update_(sb, grad[b].contiguous(), lrs[b], False, lb=lb[b], ub=ub[b], max_change=mc[b])
+        assert torch.equal(sb, s1[b])
+
+
+METHODS_ALL = ("centered", "linear", "nes", "normalized", "raw")
+
+
+def test_functional_batched_tell_equals_the_per_item_loop(monkeypatch):
+    from evotorch_b200.algorithms.functional import cem, cem_tell, pgpe, pgpe_ask, pgpe_tell
+
+    torch.manual_seed(1)
+    center = torch.randn(6, 50, device=DEV)
+    st = pgpe(center_init=center, center_learning_rate=torch.linspace(0.05, 0.2, 6), stdev_learning_rate=torch.linspace(0.05, 0.15, 6),
+              objective_sense="min", stdev_init=1.0, ranking_method="nes")
+    x = pgpe_ask(st, popsize=200)
+    ev = torch.sum(x * x, dim=-1)
+    a = pgpe_tell(st, x, ev)
+    monkeypatch.setenv("EVOTORCH_B200_FUNCTIONAL_LOOP", "1")
+    b = pgpe_tell(st, x, ev)
+    close(N(a.optimizer_state.center), N(b.optimizer_state.center), rtol=1e-5, atol=1e-6)
+    close(N(a.stdev), N(b.stdev), rtol=1e-5, atol=1e-7)
+    monkeypatch.setenv("EVOTORCH_B200_FUNCTIONAL_LOOP", "0")
+    cs = cem(center_init=center, parenthood_ratio=0.25, objective_sense="min", stdev_init=1.0, stdev_max_change=0.3)
+    a = cem_tell(cs, x, ev)
+    monkeypatch.setenv("EVOTORCH_B200_FUNCTIONAL_LOOP", "1")
+    b = cem_tell(cs, x, ev)
+    close(N(a.center), N(b.center), rtol=1e-5, atol=1e-6)
+    close(N(a.stdev), N(b.stdev), rtol=1e-5, atol=1e-7)
