@@ -470,7 +470,7 @@ def run_ours(args):
 
 
 def sharded_parity_leg(dev, use_peer: bool) -> dict:
-    """Three generations of PGPE at 100k x 1k, once row-sharded over the ranks (the collectives of the timed run) and once
+    """Three distribution updates of PGPE at 100k x 1k, once row-sharded over the ranks (the collectives of the timed run) and once
     unsharded on every rank, same seed: the first population's ranking must be IDENTICAL (same Philox counters, global
     ranking) and mu / sigma must agree to fp32 summation order."""
     import torch
@@ -512,6 +512,7 @@ def sharded_parity_leg(dev, use_peer: bool) -> dict:
     for _ in range(gens - 1):
         sh.step()
         un.step()
+    un.step()  # the single-process searcher only samples on its first step (gaussian.py:351-355); the sharded protocol updates on every step
 
     def rel(a, b):  # max-norm relative difference (element-wise ratios explode on the centre's near-zero components)
         return float((a - b).abs().max() / b.abs().max())

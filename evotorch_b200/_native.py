@@ -38,6 +38,8 @@ _SIGNATURES = {
     "evok_clipup_batched": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "evok_sigma_update_batched": (c_int, [_P, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P]),
     "evok_rank_table": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
+    "evok_cholesky_workspace_bytes": (c_size_t, [c_int64]),
+    "evok_cholesky": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "evok_cmaes_row_weights": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "evok_cmaes_vector_update": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, c_int, _P, _P, _P]),
     "evok_weights_adjust": (c_int, [_P, c_int64, c_int, _P]),

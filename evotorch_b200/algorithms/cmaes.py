@@ -12,7 +12,8 @@ kernel (csrc/evok_gemm.cu: TMA -> 128B-swizzled smem -> tcgen05.mma.kind::tf32 w
 register accumulation; the lo halves of the 3xTF32 operands are derived inside the kernel, so operands are read from HBM once); the
 glue between the contractions is fused into four small kernels (csrc/evok_cmaes.cu, evok_rank_table) and the covariance update is
 applied by the SYRK's epilogue, so a generation is ~14 launches with no host reads and replays from a CUDA graph
-(`enable_cuda_graph()`).  The Cholesky factorisation stays on cuSOLVER (torch.linalg.cholesky_ex).
+(`enable_cuda_graph()`).  The Cholesky factorisation stays on cuSOLVER (torch.linalg.cholesky_ex): the repo's own persistent
+tile-dataflow kernel (csrc/evok_chol.cu, EVOTORCH_B200_EVOK_CHOLESKY=1) is correct but measured 2.2x slower at D = 1024.
 """
 
 from __future__ import annotations
@@ -250,7 +251,12 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
             torch.diagonal(self.C)[:] = unscaled
 
     def decompose_C(self) -> None:
-        self.A = self.C.pow(0.5) if self.separable else torch.linalg.cholesky(self.C)
+        if self.separable:
+            self.A = self.C.pow(0.5)
+        elif ops.uses_kernels(self.C) and self.C.is_contiguous() and os.environ.get("EVOTORCH_B200_EVOK_CHOLESKY", "0") == "1":
+            self.A = ops.cholesky(self.C)
+        else:
+            self.A = torch.linalg.cholesky(self.C)
 
     # ------------------------------------------------------------------ fused generation (CUDA float32, full covariance)
     def _fused_ok(self) -> bool:
@@ -298,7 +304,11 @@ class CMAES(SearchAlgorithm, SinglePopulationAlgorithmMixin):
                                 steps=self._steps_count, steps_dev=fs["steps_dev"])
         ops.weighted_syrk_update(ys, fs["w_act"], fs["k"], self.C, u=self.p_c, out=self.C)
         if fs["steps_dev"] is not None or (self._steps_count + 1) % self.decompose_C_freq == 0:
-            torch.linalg.cholesky_ex(self.C, check_errors=False, out=(self.A, fs["info"]))
+            if os.environ.get("EVOTORCH_B200_EVOK_CHOLESKY", "0") == "1":
+                ops.cholesky(self.C, out=self.A)  # the repo's own tile-dataflow kernel (csrc/evok_chol.cu): correct, but measured
+                # 2.2x SLOWER than cuSOLVER's potrf at D = 1024 (0.75 vs 0.34 ms, profiles/r02_cholesky.txt), so it is not the default
+            else:
+                torch.linalg.cholesky_ex(self.C, check_errors=False, out=(self.A, fs["info"]))
 
     # ------------------------------------------------------------------ CUDA-graph replay of the fused generation
     def enable_cuda_graph(self, enabled: bool = True):

@@ -600,6 +600,24 @@ def weighted_syrk_update(Y: torch.Tensor, w: torch.Tensor, k: torch.Tensor, C: t
     return out
 
 
+def cholesky(A: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Lower Cholesky factor of a symmetric positive definite fp32 matrix (only the lower triangle of `A` is read); NaNs if `A` is not
+    positive definite.  One persistent tile-dataflow kernel (csrc/evok_chol.cu)."""
+    _mat(A, "A")
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise ValueError(f"A: expected a square matrix, got {tuple(A.shape)}")
+    out = torch.empty_like(A) if out is None else _mat(out, "out")
+    if out.data_ptr() == A.data_ptr():
+        raise ValueError("out must not alias A")
+    lib = nat.lib()
+    ws = nat.workspace(A.device, lib.evok_cholesky_workspace_bytes(n), "cholesky")
+    with _timed("cholesky"):
+        rc = lib.evok_cholesky(A.data_ptr(), A.stride(0), n, out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(), nat.stream_of(A))
+    nat.check(rc, "evok_cholesky")
+    return out
+
+
 def transpose_scale(X: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(w[:, None] * X).T as a new row-major matrix."""
     _mat(X, "X")

@@ -272,6 +272,13 @@ int evok_cmaes_vector_update(const float* local_disp, const float* shaped_disp, 
                              int64_t* steps_dev, int64_t steps_host, const float* consts_host, int csa_squared, float* k_out, float* h_sig_out,
                              void* stream);
 
+/* Cholesky factorisation A = L L^T (fp32, lower; the strictly upper part of L is zeroed, like torch.linalg.cholesky).  Replaces
+ * CMAES.decompose_C (cmaes.py:555-565, torch.linalg.cholesky -> cuSOLVER potrf).  ONE persistent kernel: 64 x 64 tiles, left-looking
+ * tile dataflow with per-tile release / acquire flags instead of a launch (or grid barrier) per panel step.  Only the lower triangle
+ * of A is read.  L must not alias A.  A matrix that is not positive definite yields NaNs (no error code: nothing is read back). */
+size_t evok_cholesky_workspace_bytes(int64_t n);
+int evok_cholesky(const float* A, int64_t lda, int64_t n, float* L, int64_t ldl, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Peer exchange over NVLink / NVSwitch: the two collectives of the sharded generation (the reference's Ray round trip,
  * core.py:2762-3073 + algorithms/distributed/gaussian.py:199-272; evotorch_b200/distributed.py) fused into their

@@ -520,3 +520,40 @@ def test_functional_batched_tell_equals_the_per_item_loop(monkeypatch):
     b = cem_tell(cs, x, ev)
     close(N(a.center), N(b.center), rtol=1e-5, atol=1e-6)
     close(N(a.stdev), N(b.stdev), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ Cholesky kernel
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 64, 65, 100, 128, 130, 257, 1000, 1024, 2048])
+def test_tile_dataflow_cholesky_matches_float64(n):
+    """evok_cholesky (cmaes.py:555-565 `decompose_C`) against numpy's float64 factorisation: L lower-triangular with zeros above
+    the diagonal, L L^T = A to fp32 accuracy; only the lower triangle of the input is read."""
+    g = torch.Generator(device=DEV).manual_seed(n)
+    B = torch.randn(n, n, device=DEV, generator=g)
+    A = (B @ B.T / n + torch.eye(n, device=DEV) * (0.5 + torch.rand(n, device=DEV, generator=g))).contiguous()
+    ref = np.linalg.cholesky(N(A).astype(np.float64))
+    L = ops.cholesky(A)
+    assert float(torch.triu(L, 1).abs().max()) == 0.0 if n > 1 else True
+    scale = float(np.abs(ref).max())
+    assert float(np.abs(N(L).astype(np.float64) - ref).max()) <= 2e-5 * scale
+    rec = (L.double() @ L.double().T - A.double()).abs().max() / A.double().abs().max()
+    assert float(rec) < 5e-6
+    # garbage above the diagonal of the input must not matter; a padded (strided) input / output works too
+    junk = A + torch.triu(torch.full_like(A, 7.0), 1)
+    assert torch.equal(ops.cholesky(junk), L)
+    wide = torch.zeros(n, n + 4, device=DEV)
+    wide[:, :n] = A
+    out = torch.full((n, n + 8), 3.0, device=DEV)
+    ops.cholesky(wide[:, :n], out=out[:, :n])
+    assert torch.equal(out[:, :n], L) and float(out[:, n:].min()) == 3.0
+    # run it twice back to back (flags are reset by every call) and against the library
+    assert torch.equal(ops.cholesky(A), L)
+    lib = torch.linalg.cholesky(A)
+    assert float((L - lib).abs().max()) <= 2e-5 * scale
+
+
+def test_cholesky_of_an_indefinite_matrix_gives_nans_not_a_hang():
+    A = torch.eye(200, device=DEV)
+    A[150, 150] = -1.0
+    L = ops.cholesky(A)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(L).any())
