@@ -515,7 +515,7 @@ class Problem(Clonable):
         return {"best": self._best, "worst": self._worst}
 
     # ------------------------------------------------------------------ pickling (core.py:2711-2734)
-    _TRANSIENT = ("_peer_exchange", "_active_peer", "_grad_batches", "_grad_scratch")
+    _TRANSIENT = ("_peer_exchange", "_active_peer", "_grad_batches", "_grad_scratch", "_d2h_stage")
 
     def __getstate__(self) -> dict:
         """Device-mapped and cached objects (peer-exchange buffers, gradient batches, the CUDA-graph generation counter) are

@@ -95,6 +95,35 @@ def broadcast_search_state(tensors: list) -> None:
                 t.copy_(c)
 
 
+def _results_to_home(problem, grads: dict, mean_eval: torch.Tensor, home_device: torch.device) -> tuple:
+    """Gradients and mean fitness on the distribution's device.  Device -> host goes through ONE packed copy into a pinned
+    staging buffer and one stream synchronisation (instead of a blocking copy per tensor)."""
+    if home_device == problem.device:
+        return grads, mean_eval
+    if home_device.type != "cpu" or problem.device.type != "cuda":
+        return {k: v.to(home_device) for k, v in grads.items()}, mean_eval.to(home_device)
+    keys = sorted(grads)
+    sizes = [grads[k].numel() for k in keys]
+    total = sum(sizes) + 1
+    stage = problem.__dict__.get("_d2h_stage")
+    if stage is None or stage[0].numel() != total:
+        stage = problem.__dict__["_d2h_stage"] = (torch.empty(total, dtype=torch.float32).pin_memory(),
+                                                  torch.empty(total, dtype=torch.float32, device=problem.device))
+    host, dev = stage
+    off = 0
+    for k, n in zip(keys, sizes):
+        dev[off:off + n].copy_(grads[k].reshape(-1))
+        off += n
+    dev[off:off + 1].copy_(mean_eval.reshape(1))
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.current_stream(problem.device).synchronize()
+    out, off = {}, 0
+    for k, n in zip(keys, sizes):
+        out[k] = host[off:off + n].clone().reshape(grads[k].shape)
+        off += n
+    return out, host[off].clone()
+
+
 def _usable_peer_exchange(problem, dev_dist, popsize: int, ws: int):
     """The PeerExchange attached to `problem` (peer.enable_peer_exchange) if this generation can run on it."""
     peer = getattr(problem, "_peer_exchange", None)
@@ -166,9 +195,7 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
             dev_dist._peer = None
         grads = dev_dist.finalize_gradients(summed, popsize)
         mean_eval = mean_buf.reshape(())  # live 1-element buffer: holds the latest generation's global mean fitness
-        if home_device != problem.device:
-            grads = {k: v.to(home_device) for k, v in grads.items()}
-            mean_eval = mean_eval.to(home_device)
+        grads, mean_eval = _results_to_home(problem, grads, mean_eval, home_device)
         return {"gradients": grads, "num_solutions": popsize, "mean_eval": mean_eval}
     if peer is not None:
         f_all = peer.wait_fitness()
@@ -196,9 +223,7 @@ def sharded_sample_and_gradients(problem, distribution, popsize: int, *, obj_ind
         grads = dev_dist._compute_gradients(samples, weights_all, method)
 
     mean_eval = torch.mean(f_all)  # 0-dim tensor: converting it to float is the caller's (lazy) choice, no forced sync here
-    if home_device != problem.device:
-        grads = {k: v.to(home_device) for k, v in grads.items()}
-        mean_eval = mean_eval.to(home_device)
+    grads, mean_eval = _results_to_home(problem, grads, mean_eval, home_device)
     return {"gradients": grads, "num_solutions": popsize, "mean_eval": mean_eval}
 
 

@@ -84,6 +84,13 @@ class Distribution(Clonable):
     def to(self, device) -> "Distribution":
         if torch.device(self.device) == torch.device(device):
             return self
+        device = torch.device(device)
+        if device.type == "cuda":
+            # host-resident distribution driving a CUDA problem (core.py:2958 `dist_on_cpu` protocol in reverse): parameters that
+            # live in pinned memory are copied asynchronously on the current stream (the kernels that consume them are ordered
+            # behind the copies), so the transfer costs no host synchronisation
+            params = {k: (v.to(device, non_blocking=v.is_pinned()) if isinstance(v, torch.Tensor) else v) for k, v in self.parameters.items()}
+            return type(self)(solution_length=self.solution_length, parameters=params, device=device)
         return type(self)(solution_length=self.solution_length, parameters=self.parameters, device=device)
 
     def modified_copy(self, *, dtype=None, device=None, **parameters) -> "Distribution":
