@@ -611,6 +611,28 @@ def other_config_legs(dev, peak_gbs: float) -> dict:
         gb = 4.0 * NP * pol.parameter_length / 1e9
         out["cfg4_mlp_376_256_17_x_65536"] = {"ms_per_forward": ms, "gbs": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / peak_gbs,
                                               "observations_per_policy": 1, "activation": "tanh", "params_per_policy": pol.parameter_length}
+        # the same population on ONE shared minibatch of 256 observations (SupervisedNE, common_minibatch): the first layer of all
+        # 65 536 networks is a single (16.8 M x 376) x (376 x 256) product on the tcgen05 GEMM (3xTF32, weights read once)
+        try:
+            Bm = 256
+            xb = torch.randn(Bm, 376, device=dev)
+            for _ in range(2):
+                y = pol.forward_shared(P, xb)
+            ms_b = timed(lambda: pol.forward_shared(P, xb), 5)
+            useful = 2.0 * NP * Bm * (376 * 256 + 256 * 17)
+            tensor = 3 * 2.0 * NP * Bm * 376 * 256
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                    tf32_peak = float(json.load(fh)["bf16_tflops"]) / 2.0
+            except Exception:
+                tf32_peak = 1100.0
+            out["cfg4_mlp_376_256_17_x_65536"]["shared_minibatch_B256"] = {
+                "ms_per_forward": ms_b, "useful_tflops_fp32_equivalent": useful / ms_b / 1e9, "tensor_tflops_3xtf32": tensor / ms_b / 1e9,
+                "frac_of_tf32_peak": tensor / ms_b / 1e9 / tf32_peak, "tf32_peak_tflops": tf32_peak, "parameter_gbs": gb / ms_b * 1e3,
+                "observations_per_policy": Bm}
+            del y, xb
+        except Exception as exc:
+            out["cfg4_mlp_376_256_17_x_65536"]["shared_minibatch_B256"] = {"error": repr(exc)[:300]}
         del P, obs, pol
         torch.cuda.empty_cache()
     except Exception as exc:

@@ -128,6 +128,14 @@ struct GemmParams {
   const float* affine_E;
   int64_t lde;
   const float* affine_u;
+  // GATHER (batched policy forward, stacked weight rows): row m of the A operand lives at
+  //   gather_a + (m / ga_rows_per_batch) * ga_batch_stride + (m % ga_rows_per_batch) * ga_row_stride     (any 4-byte alignment)
+  // and the epilogue applies  C = act(acc + row_bias[(m / rows_per_batch) * rb_batch_stride + m % rows_per_batch])
+  const float* gather_a;
+  int64_t ga_rows_per_batch, ga_batch_stride, ga_row_stride;
+  const float* row_bias;
+  int64_t rb_batch_stride;
+  int row_act;
 };
 
 // The tensor core adds every MMA into the TMEM accumulator with round-toward-zero; over hundreds of MMAs that is a
@@ -136,7 +144,19 @@ struct GemmParams {
 // register accumulators with ordinary round-to-nearest fp32 adds while the MMA warp fills the other TMEM accumulator.
 constexpr int kGemmChunk = 4;
 
-template <bool CONVERT>
+__device__ __forceinline__ float gemm_act(float v, int act) {
+  switch (act) {
+    case EVOK_ACT_TANH: return tanhf(v);
+    case EVOK_ACT_RELU: return fmaxf(v, 0.0f);
+    case EVOK_ACT_SIGMOID: return __fdiv_rn(1.0f, 1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// GATHER (implies CONVERT): the A operand is not TMA-addressable (rows only 4-byte aligned, non-uniform pitch: the stacked first-layer
+// weights of a population of flat parameter vectors); the two converter warps fetch its tile with coalesced 128-byte row loads and
+// write BOTH the raw and the lo tile in the 128-byte-swizzled layout the tensor core expects, so the weights are read from HBM once.
+template <bool CONVERT, bool GATHER = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
@@ -183,9 +203,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const uint32_t use = i / kGemmStages;
         bar_wait(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
         unsigned char* st = base + (size_t)s * kStageBytes;
-        bar_expect_tx(&full[s], CONVERT ? kTileABytes + kTileBBytes : kStageBytes);
+        bar_expect_tx(&full[s], GATHER ? kTileBBytes : (CONVERT ? kTileABytes + kTileBBytes : kStageBytes));
         const int kx = (kb_begin + i) * kGemmBK;
-        tma_load_2d(st, &map_a_hi, kx, m0, &full[s]);
+        if (!GATHER) tma_load_2d(st, &map_a_hi, kx, m0, &full[s]);
         if (!CONVERT) tma_load_2d(st + kTileABytes, &map_a_lo, kx, m0, &full[s]);
         tma_load_2d(st + 2 * kTileABytes, &map_b_hi, kx, n0, &full[s]);
         if (!CONVERT) tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
@@ -229,15 +249,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kGemmStages;
         const uint32_t use = i / kGemmStages;
-        bar_wait(&full[s], use & 1);
         unsigned char* st = base + (size_t)s * kStageBytes;
+        auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+        if (GATHER) {
+          // the stage must be free (its previous MMAs done) before it is overwritten; then 64 rows per warp, one 128-byte row
+          // segment per warp instruction; element (r, k) of a 128B-swizzled K-major tile sits at
+          //   r * 128 + ((k / 4) ^ (r % 8)) * 16 + (k % 4) * 4
+          bar_wait(&empty[s], (use & 1) ^ 1);
+          const int kcol = (kb_begin + i) * kGemmBK + lane;
+          const bool k_ok = kcol < p.K;
+          const int wrow0 = (warp - 2) * 64;
+          // row pointers advance incrementally (one division per K-block, not per row)
+          const int m_first = m0 + wrow0;
+          int hrow = m_first % (int)p.ga_rows_per_batch;
+          const float* rowp = p.gather_a + (int64_t)(m_first / (int)p.ga_rows_per_batch) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
+          const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
+#pragma unroll 8
+          for (int it = 0; it < 64; ++it) {
+            const int r = wrow0 + it;
+            float v = 0.0f;
+            if (k_ok && m0 + r < p.M) v = __ldg(rowp);
+            rowp += p.ga_row_stride;
+            if (++hrow == (int)p.ga_rows_per_batch) {
+              hrow = 0;
+              rowp += wrap;
+            }
+            const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+            *reinterpret_cast<float*>(st + off) = v;
+            *reinterpret_cast<float*>(st + kTileABytes + off) = lo_of(v);
+          }
+        }
+        bar_wait(&full[s], use & 1);
         const float4* a_raw = reinterpret_cast<const float4*>(st);
         float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
         const float4* b_raw = reinterpret_cast<const float4*>(st + 2 * kTileABytes);
         float4* b_lo = reinterpret_cast<float4*>(st + 2 * kTileABytes + kTileBBytes);
-        auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
 #pragma unroll 4
-        for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
+        for (int j = 0; j < (GATHER ? 0 : (int)(kTileABytes / 16 / 64)); ++j) {
           const float4 v = a_raw[ct + 64 * j];
           a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
         }
@@ -276,6 +324,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
     };
     for (int ch = 0; ch < num_chunks; ++ch) fold_chunk(ch);
+    if (GATHER && p.row_bias) {  // C = act(acc + bias of this row): TMEM lane = row of the tile
+      const int64_t m = (int64_t)m0 + quad * 32 + lane;
+      if (m < p.M) {
+        const int64_t bi = m / p.ga_rows_per_batch;
+        const float b = __ldg(p.row_bias + bi * p.rb_batch_stride + (m - bi * p.ga_rows_per_batch));
+#pragma unroll
+        for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = gemm_act(acc[j] + b, p.row_act);
+      }
+    }
     // all MMAs have completed (the last tmem_full has fired), so the pipeline stages are free: use them as transpose scratch
     float* stile = reinterpret_cast<float*>(base) + (size_t)(warp - 4) * (32 * kEpiPitch);
     const float alpha = (p.C2 && p.alpha_dev) ? *p.alpha_dev : 1.0f;
@@ -527,16 +584,21 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
   p.affine_E = aff ? aff->E : nullptr;
   p.lde = aff ? aff->lde : 0;
   p.affine_u = aff ? aff->u : nullptr;
+  p.gather_a = nullptr;
+  p.ga_rows_per_batch = p.ga_batch_stride = p.ga_row_stride = p.rb_batch_stride = 0;
+  p.row_bias = nullptr;
+  p.row_act = 0;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
       return (int)cudaGetLastError();
     attr_set = true;
   }
   dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((N + kGemmBN - 1) / kGemmBN), (unsigned)g.splits);
-  if (convert) gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  else gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if (convert) gemm_tf32x3_kernel<true, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else gemm_tf32x3_kernel<false, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   EVOK_CHECK_LAUNCH();
   if (split) {
     reduce_splits_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(partial, g.splits, M * N, M, N, N, C, ldc, aff ? aff->k : nullptr,
@@ -558,6 +620,43 @@ extern "C" EVOK_API int evok_gemm_nt_affine(const float* A, int64_t lda, const f
   if (!k_dev) return EVOK_E_NULLPTR;
   const GemmAffine aff{k_dev, E, lde, u};
   return gemm_impl(A, lda, B, ldb, M, N, K, C, ldc, nullptr, 0, nullptr, nullptr, &aff, ws, ws_bytes, stream);
+}
+
+// Stacked-rows GEMM of the batched policy forward:  C[(i, h), b] = act( sum_k W_i[h, k] * X[b, k] + bias_i[h] )
+// A rows gathered from the population matrix (see GemmParams::gather_a), B = the shared input batch X (n_cols x K, TMA: 16-byte aligned).
+extern "C" EVOK_API int evok_gemm_gather_rows(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch, int64_t n_batches,
+                                              const float* X, int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset, int act, float* C,
+                                              int64_t ldc, void* stream) {
+  if (!params || !X || !C) return EVOK_E_NULLPTR;
+  const int64_t M = rows_per_batch * n_batches;
+  if (rows_per_batch <= 0 || n_batches <= 0 || n_cols <= 0 || K <= 0 || ldx < K || ldc < n_cols || M >= (1ll << 31)) return EVOK_E_BADSIZE;
+  if (act < EVOK_ACT_NONE || act > EVOK_ACT_SIGMOID) return EVOK_E_BADENUM;
+  if (!tma_ok(X, ldx)) return EVOK_E_ALIGN;
+  CUtensorMap mb;
+  int rc;
+  if ((rc = make_map(&mb, X, n_cols, K, ldx, kGemmBN))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)n_cols; p.K = (int)K;
+  p.kblocks_per_split = (int)((K + kGemmBK - 1) / kGemmBK);
+  p.C = C;
+  p.ldc = ldc;
+  p.gather_a = params + w_offset;
+  p.ga_rows_per_batch = rows_per_batch;
+  p.ga_batch_stride = batch_stride;
+  p.ga_row_stride = K;
+  p.row_bias = bias_offset >= 0 ? params + bias_offset : nullptr;
+  p.rb_batch_stride = batch_stride;
+  p.row_act = act;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)
+      return (int)cudaGetLastError();
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((n_cols + kGemmBN - 1) / kGemmBN), 1);
+  gemm_tf32x3_kernel<true, true><<<grid, kGemmThreads, kGemmSmemBytes, (cudaStream_t)stream>>>(mb, mb, mb, mb, p);
+  EVOK_CHECK_LAUNCH();
+  return 0;
 }
 
 extern "C" EVOK_API int evok_transpose_pair(const float* in, int64_t ldi, int64_t rows, int64_t cols, const float* w, float* out_w, float* out_p,

@@ -169,9 +169,127 @@ __global__ void __launch_bounds__(kMlpThreads)
   }
 }
 
+// ---- shared-minibatch forward (SupervisedNE with common_minibatch, supervisedne.py:337-347): layers 2..n of N networks on B samples.
+// The first layer is the tensor-core GEMM over the stacked weight rows (evok_gemm_gather_rows), which leaves
+//   hid[(i * H1 + h) * ldh + b] = act_0(W_0^i x_b + b_0^i)[h];
+// this kernel takes one (network i, tile of 32 samples) per CTA, keeps the tile's activations in shared memory ([width][33]) and runs
+// the remaining layers with fp32 FMAs: thread = (sample lane, output neuron), the weight row is a broadcast load shared by the 32
+// samples of the warp.  out[(i * B + b) * O + o].
+constexpr int kTailSamples = 32;
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxWidth = 512;
+
+__global__ void __launch_bounds__(kTailThreads)
+    mlp_tail_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ hid, int64_t ldh, int64_t n_first, int64_t B,
+                    float* __restrict__ out, const __grid_constant__ MlpSpec spec) {
+  extern __shared__ float tail_smem[];
+  const int pitch = kTailSamples + 1;
+  float* cur = tail_smem;
+  float* nxt = tail_smem + (size_t)spec.max_width * pitch;
+  const int64_t net = blockIdx.y;
+  const int64_t b0 = (int64_t)blockIdx.x * kTailSamples;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t b = b0 + lane;
+  const bool b_ok = b < B;
+  const float* prow = params + (net + n_first) * ldp;
+  const int h1 = spec.dims[1];
+  for (int h = wid; h < h1; h += kTailThreads / 32) cur[h * pitch + lane] = b_ok ? hid[(net * h1 + h) * ldh + b] : 0.0f;
+  __syncthreads();
+  for (int l = 1; l < spec.n_layers; ++l) {
+    const int din = spec.dims[l], dout = spec.dims[l + 1];
+    const float* W = prow + spec.w_off[l];
+    const float* bias = W + (int64_t)din * dout;
+    for (int o = wid; o < dout; o += kTailThreads / 32) {
+      const float* w = W + (int64_t)o * din;
+      float s0 = 0.0f, s1 = 0.0f;
+      int k = 0;
+      for (; k + 1 < din; k += 2) {
+        s0 = fmaf(__ldg(w + k), cur[k * pitch + lane], s0);
+        s1 = fmaf(__ldg(w + k + 1), cur[(k + 1) * pitch + lane], s1);
+      }
+      if (k < din) s0 = fmaf(__ldg(w + k), cur[k * pitch + lane], s0);
+      const float v = activate(s0 + s1 + __ldg(bias + o), spec.acts[l]);
+      if (l == spec.n_layers - 1) {
+        if (b_ok) out[((net * B) + b) * dout + o] = v;
+      } else {
+        nxt[o * pitch + lane] = v;
+      }
+    }
+    __syncthreads();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+}
+
 }  // namespace evok
 
 using namespace evok;
+
+extern "C" EVOK_API size_t evok_mlp_forward_shared_workspace_bytes(int64_t N, int64_t B, int n_layers, const int32_t* dims_host) {
+  if (!dims_host || n_layers < 2 || N <= 0 || B <= 0) return 256;
+  const int64_t ldh = (B + 3) / 4 * 4;
+  int64_t chunk = ((int64_t)1 << 30) / (dims_host[1] * ldh * 4);  // about 1 GiB of first-layer activations at a time
+  if (chunk < 1) chunk = 1;
+  if (chunk > 65535) chunk = 65535;
+  if (chunk > N) chunk = N;
+  return (size_t)chunk * dims_host[1] * ldh * 4 + 256;
+}
+
+// out[i, b, :] = net_i(X[b, :]) for N flat parameter rows and ONE shared input batch X (B x dims[0], 16-byte aligned rows).
+extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp, int64_t N, const float* X, int64_t ldx, int64_t B, int n_layers,
+                                                const int32_t* dims_host, const int32_t* acts_host, float* out, void* ws, size_t ws_bytes,
+                                                void* stream) {
+  if (!params || !X || !out || !dims_host || !acts_host || !ws) return EVOK_E_NULLPTR;
+  if (n_layers < 2 || n_layers > kMlpMaxLayers || N < 0 || B <= 0) return EVOK_E_BADSIZE;
+  MlpSpec spec;
+  spec.n_layers = n_layers;
+  int64_t off = 0;
+  int maxw = 0;
+  for (int l = 0; l <= n_layers; ++l) {
+    const int d = dims_host[l];
+    if (d < 1 || d > kMlpMaxWidth) return EVOK_E_BADSIZE;
+    spec.dims[l] = d;
+    if (l >= 1 && d > maxw) maxw = d;
+  }
+  if (maxw > kTailMaxWidth) return EVOK_E_BADSIZE;
+  for (int l = 0; l < n_layers; ++l) {
+    if (acts_host[l] < EVOK_ACT_NONE || acts_host[l] > EVOK_ACT_SIGMOID) return EVOK_E_BADENUM;
+    spec.acts[l] = acts_host[l];
+    spec.w_off[l] = off;
+    off += (int64_t)spec.dims[l] * spec.dims[l + 1] + spec.dims[l + 1];
+  }
+  spec.max_width = maxw;
+  if (ldp < off || ldx < spec.dims[0]) return EVOK_E_BADSIZE;
+  if (N == 0) return 0;
+  const int64_t h1 = spec.dims[1], ldh = (B + 3) / 4 * 4;
+  int64_t chunk = ((int64_t)1 << 30) / (h1 * ldh * 4);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 65535) chunk = 65535;  // gridDim.y of the tail kernel
+  if (chunk > N) chunk = N;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)chunk * h1 * ldh * 4) return EVOK_E_WORKSPACE;
+  float* hid = reinterpret_cast<float*>(base);
+  const size_t smem = 2 * (size_t)maxw * (kTailSamples + 1) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(mlp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTailMaxWidth * (kTailSamples + 1) * sizeof(float))) !=
+        cudaSuccess)
+      return (int)cudaGetLastError();
+    attr_set = true;
+  }
+  for (int64_t i0 = 0; i0 < N; i0 += chunk) {
+    const int64_t c = (N - i0) < chunk ? (N - i0) : chunk;
+    // layer 0 of the c networks as ONE stacked-rows tensor-core product: (c * H1 x in) * (in x B)
+    int rc = evok_gemm_gather_rows(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0], spec.w_off[0] + (int64_t)spec.dims[0] * h1,
+                                   spec.acts[0], hid, ldh, stream);
+    if (rc) return rc;
+    dim3 grid((unsigned)((B + kTailSamples - 1) / kTailSamples), (unsigned)c);
+    mlp_tail_kernel<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[n_layers], spec);
+    EVOK_CHECK_LAUNCH();
+  }
+  return 0;
+}
 
 extern "C" EVOK_API int64_t evok_mlp_parameter_length(int n_layers, const int32_t* dims_host) {
   if (!dims_host || n_layers < 1 || n_layers > kMlpMaxLayers) return -1;

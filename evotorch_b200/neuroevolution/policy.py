@@ -124,10 +124,10 @@ class Policy:
         shared batch); anything else goes through `vmap(functional_call)`."""
         if parameters.ndim != 2 or parameters.shape[1] != self.parameter_length:
             raise ValueError(f"Expected parameters of shape (N, {self.parameter_length}), got {tuple(parameters.shape)}")
-        if (self._spec is not None and ops.uses_kernels(parameters) and ops.uses_kernels(x) and x.ndim == 2 and parameters.stride(1) == 1
-                and hasattr(ops, "mlp_forward_shared")):
+        if self._spec is not None and ops.uses_kernels(parameters) and ops.uses_kernels(x) and x.ndim == 2 and parameters.stride(1) == 1:
             dims, acts = self._spec
-            return ops.mlp_forward_shared(parameters, x, dims, acts)
+            if len(acts) >= 2 and max(dims[1:]) <= 512:
+                return ops.mlp_forward_shared(parameters, x.contiguous(), dims, acts)
         return vmap(self._call_one, in_dims=(0, None))(parameters, x)
 
     @torch.no_grad()

@@ -547,6 +547,38 @@ def mlp_forward(params: torch.Tensor, obs: torch.Tensor, dims, acts, out: Option
     return out
 
 
+def mlp_forward_shared(params: torch.Tensor, x: torch.Tensor, dims, acts) -> torch.Tensor:
+    """Row i of `params` (N x L flat feed-forward parameters) applied to the SHARED input batch `x` (B x in) -> N x B x out.
+    First layer: one tensor-core product of the stacked weight rows of all N networks with the batch (weights read from HBM once,
+    3xTF32 = fp32 accuracy); remaining layers: per-network fp32 kernel."""
+    import ctypes
+
+    _mat(params, "parameters"); _mat(x, "x")
+    dims = [int(d) for d in dims]
+    act_ids = [ACT_IDS[a] if isinstance(a, str) else int(a) for a in acts]
+    n, B = params.shape[0], x.shape[0]
+    if x.shape[1] != dims[0]:
+        raise ValueError(f"x: expected {dims[0]} columns, got {x.shape[1]}")
+    if len(act_ids) < 2 or max(dims[1:]) > 512:
+        raise ValueError("mlp_forward_shared handles nets with >= 2 layers and widths <= 512")
+    d_arr = (ctypes.c_int32 * len(dims))(*dims)
+    a_arr = (ctypes.c_int32 * len(act_ids))(*act_ids)
+    lib = nat.lib()
+    if params.shape[1] != lib.evok_mlp_parameter_length(len(act_ids), d_arr):
+        raise ValueError("parameters: wrong number of columns for these layer widths")
+    if x.data_ptr() % 16 != 0 or x.stride(0) % 4 != 0:  # the batch is the TMA operand: 16-byte aligned rows
+        padded = torch.zeros(B, (dims[0] + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+        padded[:, :dims[0]] = x
+        x = padded[:, :dims[0]]
+    out = torch.empty(n, B, dims[-1], dtype=torch.float32, device=params.device)
+    ws = nat.workspace(params.device, lib.evok_mlp_forward_shared_workspace_bytes(n, B, len(act_ids), d_arr) + 512, "mlp_shared")
+    with _timed("mlp_forward_shared"):
+        rc = lib.evok_mlp_forward_shared(params.data_ptr(), params.stride(0), n, x.data_ptr(), x.stride(0), B, len(act_ids), d_arr, a_arr,
+                                         out.data_ptr(), ws.data_ptr(), ws.numel(), nat.stream_of(params))
+    nat.check(rc, "evok_mlp_forward_shared")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ K6 / K7
 def gemm_nt(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None, *, out2: Optional[torch.Tensor] = None,
             alpha: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:

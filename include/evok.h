@@ -205,6 +205,21 @@ int evok_mlp_forward_prep(const float* params, int64_t ldp, const float* obs, in
                           const int64_t* obs_count_dev, float min_variance, float clip_lo, float clip_hi, const uint8_t* active,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* The forward of N networks on ONE shared input batch (B x dims[0]) -- a population scored on a common minibatch
+ * (neuroevolution/supervisedne.py:337-347, where the reference loops over the solutions: parameterize_net + network(x), neproblem.py:342,
+ * supervisedne.py:250).  Here the first layer of ALL networks is one tensor-core product of the stacked weight rows with the shared batch
+ * (evok_gemm_gather_rows: the weight rows are gathered from the flat parameter rows -- any 4-byte alignment -- straight into the swizzled
+ * operand tiles, so every parameter is read from HBM once; bias and activation in the epilogue), the remaining (small, per-network)
+ * layers run in a second kernel on the staged activations.  out: [N][B][dims[n_layers]].  n_layers >= 2, hidden widths <= 512,
+ * X 16-byte aligned with ldx % 4 == 0. */
+size_t evok_mlp_forward_shared_workspace_bytes(int64_t N, int64_t B, int n_layers, const int32_t* dims_host);
+int evok_mlp_forward_shared(const float* params, int64_t ldp, int64_t N, const float* X, int64_t ldx, int64_t B, int n_layers,
+                            const int32_t* dims_host, const int32_t* acts_host, float* out, void* ws, size_t ws_bytes, void* stream);
+/* C[(i, h), b] = act(sum_k W_i[h, k] X[b, k] + bias_i[h]),  W_i = params + i * batch_stride + w_offset (rows_per_batch x K, row-major),
+ * bias_i = params + i * batch_stride + bias_offset (bias_offset < 0: none).  3xTF32 on tcgen05, fp32 accuracy. */
+int evok_gemm_gather_rows(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch, int64_t n_batches, const float* X,
+                          int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset, int act, float* C, int64_t ldc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K6 / K7: fp32-accurate tensor-core GEMM (tcgen05 + TMEM + TMA, 3xTF32 operand splitting).
  *   C[M x N] = A[M x K] * B[N x K]^T        A, B, C row-major fp32 (lda, ldb >= K; ldc >= N)

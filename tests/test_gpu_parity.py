@@ -557,3 +557,45 @@ def test_cholesky_of_an_indefinite_matrix_gives_nans_not_a_hang():
     L = ops.cholesky(A)
     torch.cuda.synchronize()
     assert bool(torch.isnan(L).any())
+
+
+# ------------------------------------------------------------------------------------------------ shared-minibatch policy forward
+@pytest.mark.parametrize("dims,acts,n,B", [((376, 256, 17), ("tanh", "none"), 300, 70), ((6, 16, 3), ("relu", "none"), 1000, 256),
+                                           ((33, 40, 24, 5), ("tanh", "sigmoid", "none"), 97, 31), ((8, 512, 2), ("none", "tanh"), 64, 300)])
+def test_shared_minibatch_forward_matches_float64_and_vmap(dims, acts, n, B):
+    """`Policy.forward_shared` on CUDA (first layer = tensor-core product of the stacked weight rows, gathered from odd-length,
+    4-byte-aligned parameter rows) against a float64 evaluation of the same networks and against vmap(functional_call)
+    (what `SupervisedNE` costs the reference per solution: supervisedne.py:250, neproblem.py:342-363)."""
+    from evotorch_b200.neuroevolution import Policy
+
+    layers = []
+    for l in range(len(acts)):
+        layers.append(torch.nn.Linear(dims[l], dims[l + 1]))
+        if acts[l] != "none":
+            layers.append({"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU, "sigmoid": torch.nn.Sigmoid}[acts[l]]())
+    pol = Policy(torch.nn.Sequential(*layers).to(DEV))
+    g = torch.Generator(device=DEV).manual_seed(n + B)
+    P = torch.randn(n, pol.parameter_length, device=DEV, generator=g) * 0.3
+    x = torch.randn(B, dims[0], device=DEV, generator=g)
+    y = pol.forward_shared(P, x)
+    assert y.shape == (n, B, dims[-1])
+    # float64 reference
+    h = x.double().unsqueeze(0).expand(n, B, dims[0])
+    off = 0
+    for l in range(len(acts)):
+        W = P[:, off:off + dims[l] * dims[l + 1]].double().view(n, dims[l + 1], dims[l])
+        off += dims[l] * dims[l + 1]
+        b = P[:, off:off + dims[l + 1]].double()
+        off += dims[l + 1]
+        h = torch.einsum("nbi,noi->nbo", h, W) + b[:, None, :]
+        h = {"tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid, "none": lambda t: t}[acts[l]](h)
+    scale = float(h.abs().max())
+    assert float((y.double() - h).abs().max()) <= 3e-6 * max(scale, 1.0) + 1e-6
+    ref = torch.vmap(pol._call_one, in_dims=(0, None))(P, x)
+    assert float((y - ref).abs().max()) <= 2e-5 * max(scale, 1.0)
+    # a padded (strided) population and a strided batch give the same bits
+    wideP = torch.zeros(n, pol.parameter_length + 3, device=DEV)
+    wideP[:, :pol.parameter_length] = P
+    widex = torch.zeros(B, dims[0] + 5, device=DEV)
+    widex[:, :dims[0]] = x
+    assert torch.equal(pol.forward_shared(wideP[:, :pol.parameter_length], widex[:, :dims[0]]), y)
