@@ -136,6 +136,7 @@ struct GemmParams {
   const float* row_bias;
   int64_t rb_batch_stride;
   int row_act;
+  int debug;  // measurement only (EVOK_GATHER_DEBUG): 1 = skip the global loads of the gather, 2 = skip bias / activation
 };
 
 // The tensor core adds every MMA into the TMEM accumulator with round-toward-zero; over hundreds of MMAs that is a
@@ -144,7 +145,7 @@ struct GemmParams {
 // register accumulators with ordinary round-to-nearest fp32 adds while the MMA warp fills the other TMEM accumulator.
 constexpr int kGemmChunk = 4;
 
-__device__ __forceinline__ float gemm_act(float v, int act) {
+__device__ __noinline__ float gemm_act(float v, int act) {
   switch (act) {
     case EVOK_ACT_TANH: return tanhf(v);
     case EVOK_ACT_RELU: return fmaxf(v, 0.0f);
@@ -246,38 +247,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // the tensor core (async proxy) and signal the MMA warp.  Runs one or two K-blocks ahead of the MMAs.
     if (CONVERT) {
       const int ct = threadIdx.x - 64;  // 0 .. 63
+      auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+      // GATHER: the A tile of K-block i is fetched with 4-byte cp.async copies (global -> shared, no registers, zero fill outside
+      // the matrix): one 128-byte row segment per warp instruction, 64 rows per warp, all in flight at once; element (r, k) of a
+      // 128B-swizzled K-major tile sits at  r * 128 + ((k / 4) ^ (r % 8)) * 16 + (k % 4) * 4.  The copy of block i + 1 is issued
+      // right after block i has been converted, so a 16 KB tile per SM is in flight while the tensor core works on block i.
+      auto issue_gather = [&](int i) {
+        const int s = i % kGemmStages;
+        const uint32_t use = i / kGemmStages;
+        bar_wait(&empty[s], (use & 1) ^ 1);  // the stage's previous MMAs are done
+        const uint32_t st_a = s32(base + (size_t)s * kStageBytes);
+        const int kcol = (kb_begin + i) * kGemmBK + lane;
+        const bool k_ok = kcol < p.K;
+        const int wrow0 = (warp - 2) * 64;
+        const int m_first = m0 + wrow0;
+        int hrow = m_first % (int)p.ga_rows_per_batch;
+        const float* rowp = p.gather_a + (int64_t)(m_first / (int)p.ga_rows_per_batch) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
+        const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
+#pragma unroll 8
+        for (int it = 0; it < 64; ++it) {
+          const int r = wrow0 + it;
+          const bool ok = k_ok && (m0 + r < p.M) && p.debug != 1;
+          const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+          const float* src = ok ? rowp : p.gather_a;  // a valid address even when nothing is read (src-size 0 -> zero fill)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st_a + off), "l"(src), "r"(ok ? 4 : 0) : "memory");
+          rowp += p.ga_row_stride;
+          if (++hrow == (int)p.ga_rows_per_batch) {
+            hrow = 0;
+            rowp += wrap;
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (GATHER && num_kb > 0) issue_gather(0);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kGemmStages;
         const uint32_t use = i / kGemmStages;
         unsigned char* st = base + (size_t)s * kStageBytes;
-        auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
         if (GATHER) {
-          // the stage must be free (its previous MMAs done) before it is overwritten; then 64 rows per warp, one 128-byte row
-          // segment per warp instruction; element (r, k) of a 128B-swizzled K-major tile sits at
-          //   r * 128 + ((k / 4) ^ (r % 8)) * 16 + (k % 4) * 4
-          bar_wait(&empty[s], (use & 1) ^ 1);
-          const int kcol = (kb_begin + i) * kGemmBK + lane;
-          const bool k_ok = kcol < p.K;
-          const int wrow0 = (warp - 2) * 64;
-          // row pointers advance incrementally (one division per K-block, not per row)
-          const int m_first = m0 + wrow0;
-          int hrow = m_first % (int)p.ga_rows_per_batch;
-          const float* rowp = p.gather_a + (int64_t)(m_first / (int)p.ga_rows_per_batch) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
-          const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
-#pragma unroll 8
-          for (int it = 0; it < 64; ++it) {
-            const int r = wrow0 + it;
-            float v = 0.0f;
-            if (k_ok && m0 + r < p.M) v = __ldg(rowp);
-            rowp += p.ga_row_stride;
-            if (++hrow == (int)p.ga_rows_per_batch) {
-              hrow = 0;
-              rowp += wrap;
-            }
-            const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
-            *reinterpret_cast<float*>(st + off) = v;
-            *reinterpret_cast<float*>(st + kTileABytes + off) = lo_of(v);
-          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's copies of block i have landed
+          asm volatile("bar.sync 1, 64;" ::: "memory");         // ... and so have the other converter warp's
         }
         bar_wait(&full[s], use & 1);
         const float4* a_raw = reinterpret_cast<const float4*>(st);
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const float4* b_raw = reinterpret_cast<const float4*>(st + 2 * kTileABytes);
         float4* b_lo = reinterpret_cast<float4*>(st + 2 * kTileABytes + kTileBBytes);
 #pragma unroll 4
-        for (int j = 0; j < (GATHER ? 0 : (int)(kTileABytes / 16 / 64)); ++j) {
+        for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
           const float4 v = a_raw[ct + 64 * j];
           a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
         }
@@ -297,6 +306,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv[s])) : "memory");
+        // the next block's copy is issued AFTER this block has been handed to the tensor core (its stage frees up when the MMAs of
+        // block i - 1 retire, which overlaps with the MMAs of block i)
+        if (GATHER && i + 1 < num_kb) issue_gather(i + 1);
       }
     }
   } else {
@@ -324,13 +336,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
     };
     for (int ch = 0; ch < num_chunks; ++ch) fold_chunk(ch);
-    if (GATHER && p.row_bias) {  // C = act(acc + bias of this row): TMEM lane = row of the tile
+    if (GATHER && p.row_bias && p.debug != 2) {  // C = act(acc + bias of this row): TMEM lane = row of the tile
       const int64_t m = (int64_t)m0 + quad * 32 + lane;
       if (m < p.M) {
         const int64_t bi = m / p.ga_rows_per_batch;
         const float b = __ldg(p.row_bias + bi * p.rb_batch_stride + (m - bi * p.ga_rows_per_batch));
+        // the activation switch is hoisted out of the unrolled loop: one 128-fold copy of ONE activation per branch, the common
+        // NONE case is a plain add (a per-element switch with an inlined tanhf was 15 k instructions: instruction-cache bound)
+        if (p.row_act == EVOK_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = gemm_act(acc[j] + b, p.row_act);
+          for (int j = 0; j < kGemmBN / 2; ++j) acc[j] += b;
+        } else if (p.row_act == EVOK_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = fmaxf(acc[j] + b, 0.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = gemm_act(acc[j] + b, p.row_act);  // 128 calls of the out-of-line function
+        }
       }
     }
     // all MMAs have completed (the last tmem_full has fired), so the pipeline stages are free: use them as transpose scratch
@@ -588,6 +610,7 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
   p.ga_rows_per_batch = p.ga_batch_stride = p.ga_row_stride = p.rb_batch_stride = 0;
   p.row_bias = nullptr;
   p.row_act = 0;
+  p.debug = 0;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
@@ -647,6 +670,10 @@ extern "C" EVOK_API int evok_gemm_gather_rows(const float* params, int64_t batch
   p.row_bias = bias_offset >= 0 ? params + bias_offset : nullptr;
   p.rb_batch_stride = batch_stride;
   p.row_act = act;
+  {
+    const char* e = getenv("EVOK_GATHER_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess)

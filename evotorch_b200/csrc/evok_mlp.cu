@@ -178,14 +178,40 @@ __global__ void __launch_bounds__(kMlpThreads)
 constexpr int kTailSamples = 32;
 constexpr int kTailThreads = 256;
 constexpr int kTailMaxWidth = 512;
+constexpr int kTailOutBlock = 4;  // outputs per thread per pass (register blocking over the weight rows)
 
+// tanh to ~1e-6 absolute: odd polynomial near 0, (1 - e) / (1 + e) with e = exp(-2|x|) elsewhere.  The accurate tanhf costs ~50
+// instructions; 65 536 networks x 256 hidden units x 256 samples of them were a third of the forward.
+__device__ __forceinline__ float tanh_1e6(float x) {
+  const float ax = fabsf(x);
+  float r;
+  if (ax < 0.25f) {
+    const float t = ax * ax;
+    r = ax * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.021869488f, -0.053968254f), 0.13333334f), -0.33333334f), 1.0f);
+  } else {
+    const float e = __expf(-2.0f * ax);
+    r = __fdividef(1.0f - e, 1.0f + e);
+  }
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float activate_fast(float v, int act) {
+  switch (act) {
+    case EVOK_ACT_TANH: return tanh_1e6(v);
+    case EVOK_ACT_RELU: return fmaxf(v, 0.0f);
+    case EVOK_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-v));
+    default: return v;
+  }
+}
+
+// hid holds the first layer's PRE-activation (W_0 x + b_0); its activation is applied while the tile is loaded.
 __global__ void __launch_bounds__(kTailThreads)
     mlp_tail_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ hid, int64_t ldh, int64_t n_first, int64_t B,
                     float* __restrict__ out, const __grid_constant__ MlpSpec spec) {
   extern __shared__ float tail_smem[];
   const int pitch = kTailSamples + 1;
   float* cur = tail_smem;
-  float* nxt = tail_smem + (size_t)spec.max_width * pitch;
+  float* nxt = cur + (size_t)spec.max_width * pitch;
+  float* wsm = nxt + (size_t)spec.max_width * pitch;  // the current layer's weights + bias, staged once per CTA
   const int64_t net = blockIdx.y;
   const int64_t b0 = (int64_t)blockIdx.x * kTailSamples;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -193,32 +219,92 @@ __global__ void __launch_bounds__(kTailThreads)
   const bool b_ok = b < B;
   const float* prow = params + (net + n_first) * ldp;
   const int h1 = spec.dims[1];
-  for (int h = wid; h < h1; h += kTailThreads / 32) cur[h * pitch + lane] = b_ok ? hid[(net * h1 + h) * ldh + b] : 0.0f;
-  __syncthreads();
+  for (int h = wid; h < h1; h += kTailThreads / 32) cur[h * pitch + lane] = b_ok ? activate_fast(hid[(net * h1 + h) * ldh + b], spec.acts[0]) : 0.0f;
   for (int l = 1; l < spec.n_layers; ++l) {
     const int din = spec.dims[l], dout = spec.dims[l + 1];
     const float* W = prow + spec.w_off[l];
-    const float* bias = W + (int64_t)din * dout;
-    for (int o = wid; o < dout; o += kTailThreads / 32) {
-      const float* w = W + (int64_t)o * din;
-      float s0 = 0.0f, s1 = 0.0f;
-      int k = 0;
-      for (; k + 1 < din; k += 2) {
-        s0 = fmaf(__ldg(w + k), cur[k * pitch + lane], s0);
-        s1 = fmaf(__ldg(w + k + 1), cur[(k + 1) * pitch + lane], s1);
+    const int wcount = din * dout + dout;
+    __syncthreads();  // cur complete; wsm free
+    for (int e = threadIdx.x; e < wcount; e += kTailThreads) wsm[e] = __ldg(W + e);
+    __syncthreads();
+    const float* bias = wsm + (size_t)din * dout;
+    // thread = (sample lane, block of kTailOutBlock consecutive outputs): per k one activation load + kTailOutBlock broadcast weight loads
+    const int ob = min(kTailOutBlock, (dout + kTailThreads / 32 - 1) / (kTailThreads / 32));  // outputs per warp pass: spread dout over the 8 warps
+    for (int o0 = wid * ob; o0 < dout; o0 += (kTailThreads / 32) * ob) {
+      float acc[kTailOutBlock];
+#pragma unroll
+      for (int j = 0; j < kTailOutBlock; ++j) acc[j] = 0.0f;
+      const int nj = min(ob, dout - o0);
+#pragma unroll 4
+      for (int k = 0; k < din; ++k) {
+        const float a = cur[k * pitch + lane];
+#pragma unroll
+        for (int j = 0; j < kTailOutBlock; ++j)
+          if (j < nj) acc[j] = fmaf(wsm[(size_t)(o0 + j) * din + k], a, acc[j]);
       }
-      if (k < din) s0 = fmaf(__ldg(w + k), cur[k * pitch + lane], s0);
-      const float v = activate(s0 + s1 + __ldg(bias + o), spec.acts[l]);
-      if (l == spec.n_layers - 1) {
-        if (b_ok) out[((net * B) + b) * dout + o] = v;
-      } else {
-        nxt[o * pitch + lane] = v;
+#pragma unroll
+      for (int j = 0; j < kTailOutBlock; ++j) {
+        if (j < nj) {
+          const float v = activate_fast(acc[j] + bias[o0 + j], spec.acts[l]);
+          if (l == spec.n_layers - 1) {
+            if (b_ok) out[((net * B) + b) * dout + o0 + j] = v;
+          } else {
+            nxt[(o0 + j) * pitch + lane] = v;
+          }
+        }
       }
     }
-    __syncthreads();
     float* t = cur;
     cur = nxt;
     nxt = t;
+  }
+}
+
+// Two-layer nets with a narrow output (the usual policy / regression shape, e.g. 376-256-17): ONE CTA per network.  The second
+// layer's weights are staged once in shared memory; a warp owns 64 samples (two per lane), streams the hidden pre-activations
+// hid[h][b] straight from global memory (coalesced along b, each read exactly once), applies act_0 and accumulates all outputs
+// in registers: per hidden unit one load, one activation and dout broadcast weight reads serving 2 x dout FMAs.
+constexpr int kTail2MaxOut = 32;
+
+template <int DOUT_MAX>
+__global__ void __launch_bounds__(kTailThreads)
+    mlp_tail2_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ hid, int64_t ldh, int64_t n_first, int64_t B,
+                     float* __restrict__ out, const __grid_constant__ MlpSpec spec) {
+  extern __shared__ float tail_smem[];
+  const int64_t net = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int h1 = spec.dims[1], dout = spec.dims[2];
+  const float* W = params + (net + n_first) * ldp + spec.w_off[1];
+  for (int e = threadIdx.x; e < h1 * dout + dout; e += kTailThreads) tail_smem[e] = __ldg(W + e);
+  __syncthreads();
+  const float* bias = tail_smem + (size_t)h1 * dout;
+  const float* hrow = hid + net * h1 * ldh;
+  for (int64_t b0 = (int64_t)wid * 64; b0 < B; b0 += (kTailThreads / 32) * 64) {
+    const int64_t ba = b0 + lane, bb = b0 + 32 + lane;
+    const bool oka = ba < B, okb = bb < B;
+    float acca[DOUT_MAX], accb[DOUT_MAX];
+#pragma unroll
+    for (int o = 0; o < DOUT_MAX; ++o) acca[o] = accb[o] = 0.0f;
+#pragma unroll 2
+    for (int h = 0; h < h1; ++h) {
+      const float xa = oka ? activate_fast(__ldg(hrow + (int64_t)h * ldh + ba), spec.acts[0]) : 0.0f;
+      const float xb = okb ? activate_fast(__ldg(hrow + (int64_t)h * ldh + bb), spec.acts[0]) : 0.0f;
+#pragma unroll
+      for (int o = 0; o < DOUT_MAX; ++o) {
+        if (o < dout) {
+          const float w = tail_smem[o * h1 + h];
+          acca[o] = fmaf(w, xa, acca[o]);
+          accb[o] = fmaf(w, xb, accb[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < DOUT_MAX; ++o) {
+      if (o < dout) {
+        if (oka) out[(net * B + ba) * dout + o] = activate_fast(acca[o] + bias[o], spec.acts[1]);
+        if (okb) out[(net * B + bb) * dout + o] = activate_fast(accb[o] + bias[o], spec.acts[1]);
+      }
+    }
   }
 }
 
@@ -270,22 +356,40 @@ extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)chunk * h1 * ldh * 4) return EVOK_E_WORKSPACE;
   float* hid = reinterpret_cast<float*>(base);
-  const size_t smem = 2 * (size_t)maxw * (kTailSamples + 1) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(mlp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTailMaxWidth * (kTailSamples + 1) * sizeof(float))) !=
-        cudaSuccess)
-      return (int)cudaGetLastError();
-    attr_set = true;
+  size_t wmax = 0;  // largest staged layer (weights + bias) among the layers 1 .. n-1
+  for (int l = 1; l < n_layers; ++l) {
+    const size_t wl = (size_t)spec.dims[l] * spec.dims[l + 1] + spec.dims[l + 1];
+    if (wl > wmax) wmax = wl;
+  }
+  const size_t smem = (2 * (size_t)maxw * (kTailSamples + 1) + wmax) * sizeof(float);
+  if (smem > 200 * 1024) return EVOK_E_BADSIZE;  // a hidden layer too wide to stage: the caller falls back to the generic path
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(mlp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return (int)cudaGetLastError();
+    attr_smem = smem;
   }
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t c = (N - i0) < chunk ? (N - i0) : chunk;
     // layer 0 of the c networks as ONE stacked-rows tensor-core product: (c * H1 x in) * (in x B)
     int rc = evok_gemm_gather_rows(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0], spec.w_off[0] + (int64_t)spec.dims[0] * h1,
-                                   spec.acts[0], hid, ldh, stream);
+                                   EVOK_ACT_NONE /* act_0 is applied by the tail kernel while it loads the tile */, hid, ldh, stream);
     if (rc) return rc;
-    dim3 grid((unsigned)((B + kTailSamples - 1) / kTailSamples), (unsigned)c);
-    mlp_tail_kernel<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[n_layers], spec);
+    if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut) {
+      const size_t smem2 = ((size_t)h1 * spec.dims[2] + spec.dims[2]) * sizeof(float);
+      if (spec.dims[2] <= 8) {
+        cudaFuncSetAttribute(mlp_tail2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        mlp_tail2_kernel<8><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
+      } else if (spec.dims[2] <= 17) {
+        cudaFuncSetAttribute(mlp_tail2_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        mlp_tail2_kernel<17><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
+      } else {
+        cudaFuncSetAttribute(mlp_tail2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        mlp_tail2_kernel<32><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
+      }
+    } else {
+      dim3 grid((unsigned)((B + kTailSamples - 1) / kTailSamples), (unsigned)c);
+      mlp_tail_kernel<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[n_layers], spec);
+    }
     EVOK_CHECK_LAUNCH();
   }
   return 0;
