@@ -99,8 +99,8 @@ class PicklingLogger(Logger):
     uninterrupted one)."""
 
     def __init__(self, searcher, *, interval: int, directory: Optional[str] = None, prefix: Optional[str] = None, zfill: int = 6,
-                 items_to_save: Union[str, Iterable[str]] = ("center", "best"), after_first_step: bool = False, verbose: bool = True,
-                 checkpoint: bool = False):
+                 items_to_save: Union[str, Iterable[str]] = ("center", "best"), make_policy_from: Optional[str] = None,
+                 after_first_step: bool = False, verbose: bool = True, checkpoint: bool = False):
         super().__init__(searcher, interval=interval, after_first_step=after_first_step)
         self._searcher_ref = weakref.ref(searcher)
         self._items_to_save = (items_to_save,) if isinstance(items_to_save, str) else tuple(items_to_save)
@@ -111,6 +111,7 @@ class PicklingLogger(Logger):
         if self._directory is not None:
             os.makedirs(self._directory, exist_ok=True)
         self._verbose, self._zfill, self._checkpoint = bool(verbose), int(zfill), bool(checkpoint)
+        self._make_policy_from = None if make_policy_from is None else str(make_policy_from)
         self._last_generation: Optional[int] = None
         self._last_file_name: Optional[str] = None
 
@@ -144,6 +145,25 @@ class PicklingLogger(Logger):
             return None
         status = searcher.status
         data = {k: self._as_cpu(status[k]) for k in self._items_to_save if k in status}
+        # neuro-evolution problems: the observation statistics and a ready-to-use policy go into the file too (logging.py:297-351)
+        problem = searcher.problem
+        if hasattr(problem, "observation_normalization") and hasattr(problem, "get_observation_stats") and problem.observation_normalization:
+            stats = problem.get_observation_stats()
+            data["obs_stats"] = stats.to("cpu") if hasattr(stats, "to") else stats
+        if hasattr(problem, "to_policy"):
+            if self.__dict__.get("_make_policy_from") is None:
+                if "center" in status:
+                    policy_key = "center"
+                elif "pop_best" in status:
+                    policy_key = "pop_best"
+                else:
+                    raise ValueError("PicklingLogger did not receive an explicit value for its `make_policy_from` argument."
+                                     " The status dictionary of the search algorithm has neither 'center' nor 'pop_best'."
+                                     " Therefore, it is not clear which status item is to be used for making a policy."
+                                     " Please try instantiating a PicklingLogger with an explicit `make_policy_from` value.")
+            else:
+                policy_key = self._make_policy_from
+            data["policy"] = problem.to_policy(status[policy_key]).to("cpu")
         begun = searcher.first_step_datetime
         if begun is not None:
             now = datetime.now()

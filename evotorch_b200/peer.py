@@ -114,8 +114,11 @@ class PeerExchange:
 
     def wait_fitness(self) -> torch.Tensor:
         """Block the stream until every rank's fitness slice has landed in the local `f_all`."""
-        nat.check(nat.lib().evok_peer_wait(self._flags_f_ptr, self.world, self.epoch_f, self._counter(3), self.timeout_ns,
-                                           nat.stream_of(self.f_all)), "evok_peer_wait")
+        from . import ops
+
+        with ops._timed("peer_wait"):
+            rc = nat.lib().evok_peer_wait(self._flags_f_ptr, self.world, self.epoch_f, self._counter(3), self.timeout_ns, nat.stream_of(self.f_all))
+        nat.check(rc, "evok_peer_wait")
         return self.f_all
 
     def rank_sharded(self, f_local: torch.Tensor, method: str, higher_is_better: bool, row_offsets: list, w_local: torch.Tensor) -> tuple:
@@ -129,18 +132,23 @@ class PeerExchange:
         n_local = f_local.numel()
         offs = (ctypes.c_int64 * (self.world + 1))(*row_offsets)
         ws = nat.workspace(self.device, lib.evok_rank_workspace_bytes(max(n_local, 1)), "rank_sharded")
-        nat.check(lib.evok_rank_sharded(ops.RANK_IDS[method], f_local.data_ptr(), self.popsize, int(bool(higher_is_better)), self.world, self.rank,
-                                        offs, self.peer_keys, self.peer_fsum, self.peer_flags_f, self.epoch_f, self._rank_counters.data_ptr(),
-                                        self._counter(3), self.timeout_ns, w_local.data_ptr(), self._mean_eval.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), nat.stream_of(f_local)), "evok_rank_sharded")
+        with ops._timed("rank"):
+            rc = lib.evok_rank_sharded(ops.RANK_IDS[method], f_local.data_ptr(), self.popsize, int(bool(higher_is_better)), self.world, self.rank,
+                                       offs, self.peer_keys, self.peer_fsum, self.peer_flags_f, self.epoch_f, self._rank_counters.data_ptr(),
+                                       self._counter(3), self.timeout_ns, w_local.data_ptr(), self._mean_eval.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), nat.stream_of(f_local))
+        nat.check(rc, "evok_rank_sharded")
         return w_local, self._mean_eval
 
     def reduce_gradients(self) -> tuple:
         """Wait for every rank's slot, sum them in rank order -> (grad_mu, grad_sigma) views of `self.reduced`."""
         d = self.solution_length
-        nat.check(nat.lib().evok_peer_reduce(self.slots.data_ptr(), self.world, 2 * d, self._flags_g_ptr, self.epoch_g, self._counter(2),
-                                             self._counter(3), self.timeout_ns, self.reduced.data_ptr(), nat.stream_of(self.reduced)),
-                  "evok_peer_reduce")
+        from . import ops
+
+        with ops._timed("peer_reduce"):
+            rc = nat.lib().evok_peer_reduce(self.slots.data_ptr(), self.world, 2 * d, self._flags_g_ptr, self.epoch_g, self._counter(2),
+                                            self._counter(3), self.timeout_ns, self.reduced.data_ptr(), nat.stream_of(self.reduced))
+        nat.check(rc, "evok_peer_reduce")
         return self.reduced[:d], self.reduced[d:]
 
     def timed_out(self) -> bool:
