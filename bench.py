@@ -136,10 +136,14 @@ def cpu_reference_run(args, *, sizes, budget_s: float, max_steps: int, with_gpu_
         a = my - b * mx
     else:
         a, b = 0.0, ys[0] / xs[0]
+    fit_kind = "t(N) = a + b*N seconds per generation, least squares over the medians"
+    if a < 0.0 or b <= 0.0:  # noisy tiny samples: a negative fixed cost is unphysical -> line through the origin
+        a, b = 0.0, sum(x * y for x, y in zip(xs, ys)) / sum(x * x for x in xs)
+        fit_kind = "t(N) = b*N (least squares through the origin: the unconstrained fit had a negative intercept or slope)"
     resid = max(abs((a + b * x) - y) / y for x, y in zip(xs, ys))
     t_full = a + b * args.popsize
     prop = ys[-1] * args.popsize / xs[-1]  # plain proportional scaling of the largest sample, for comparison
-    linearity = {"fit": "t(N) = a + b*N seconds per generation, least squares over the medians", "a_s": a, "b_s_per_row": b,
+    linearity = {"fit": fit_kind, "a_s": a, "b_s_per_row": b,
                  "max_rel_residual": resid, "extrapolated_s_per_generation": t_full, "proportional_from_largest_s": prop,
                  "per_row_us": [1e6 * y / x for x, y in zip(xs, ys)]}
     torch_eager_gpu = None
