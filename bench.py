@@ -596,6 +596,13 @@ def other_config_legs(dev, peak_gbs: float) -> dict:
                                          "useful_tflops": flops / ms / 1e9, "tensor_flop_per_generation_3xtf32": 3 * 2.0 * n * d * d * 2,
                                          "frac_of_tf32_peak_3x": 3 * 2.0 * n * d * d * 2 / ms / 1e9 / tf32_peak, "tf32_peak_tflops": tf32_peak,
                                          "mean_eval": float(c.status["mean_eval"])}
+        c.enable_cuda_graph()  # the same generation replayed from one CUDA graph (cuSOLVER Cholesky included)
+        for _ in range(3):
+            c.step()
+        if c._graph is not None:
+            ms_g = timed(c.step, 20)
+            out["cfg3_cmaes_1024_x_4096"].update({"cuda_graph_generations_per_s": 1e3 / ms_g, "cuda_graph_ms_per_step": ms_g,
+                                                  "cuda_graph_frac_of_tf32_peak_3x": 3 * 2.0 * n * d * d * 2 / ms_g / 1e9 / tf32_peak})
         del c
         torch.cuda.empty_cache()
     except Exception as exc:
