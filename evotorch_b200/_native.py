@@ -72,6 +72,7 @@ _SIGNATURES = {
     "evok_peer_free": (c_int, [_P]),
     "evok_sample_eval_push": (c_int, [c_int, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint64, _P, c_int, c_int, _P, _P,
                                       _P, _P, _P]),
+    "evok_peer_push": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "evok_peer_wait": (c_int, [_P, c_int, _P, _P, c_uint64, _P]),
     "evok_grad_push": (c_int, [c_int, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_uint64, c_uint64, _P, c_float, c_float, c_int, c_int,
                                _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -39,6 +39,35 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const unsigned long long*
   if (threadIdx.x == 0) *epoch = want;
 }
 
+// One CTA per destination GPU: copy this rank's slice into that peer's buffer with 16-byte stores, then ONE system fence and the
+// flag.  Pushing the fitnesses from inside the sampler costs every one of its 444 CTAs a system-scope fence behind scattered 4-byte
+// remote stores (+68 us on a 0.86 ms kernel at 8 GPUs, measured); a dedicated 8-CTA kernel right behind the sampler moves the same
+// 500 KB per peer as coalesced vectors and fences 8 times.
+constexpr int kPushThreads = 1024;
+
+__global__ void __launch_bounds__(kPushThreads)
+    peer_push_kernel(const unsigned char* __restrict__ src, int64_t n_bytes, int64_t dst_offset, const __grid_constant__ PeerSink sink,
+                     const unsigned long long* epoch) {
+  const int p = (sink.rank + 1 + blockIdx.x) % sink.world;  // rotated: the GPUs do not all start on the same link
+  unsigned char* dst = static_cast<unsigned char*>(sink.data[p]) + dst_offset;
+  if (dst != src) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    if (vec) {
+      const int64_t nq = n_bytes >> 4;
+      for (int64_t q = threadIdx.x; q < nq; q += kPushThreads) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+      for (int64_t i = (nq << 4) + threadIdx.x; i < n_bytes; i += kPushThreads) dst[i] = src[i];
+    } else {
+      const int64_t nw = n_bytes >> 2;  // slices are made of 4-byte elements
+      for (int64_t q = threadIdx.x; q < nw; q += kPushThreads) reinterpret_cast<uint32_t*>(dst)[q] = reinterpret_cast<const uint32_t*>(src)[q];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(sink.flags[p] + sink.rank, *epoch + 1ull);
+  }
+}
+
 constexpr int kReduceThreads = 256;
 
 __global__ void __launch_bounds__(kReduceThreads)
@@ -111,6 +140,24 @@ extern "C" EVOK_API int evok_peer_reduce(const float* slots_local, int world, in
   peer_reduce_kernel<<<(unsigned)((n + kReduceThreads - 1) / kReduceThreads), kReduceThreads, 0, (cudaStream_t)stream>>>(
       slots_local, world, n, reinterpret_cast<const unsigned long long*>(flags_local), reinterpret_cast<unsigned long long*>(epoch_dev), done_dev,
       err_dev, timeout_ns, out);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API int evok_peer_push(const void* src_local, int64_t n_bytes, int64_t dst_offset_bytes, int world, int rank, void* const* peer_base_host,
+                                       void* const* peer_flags_host, const uint64_t* epoch_dev, void* stream) {
+  if (!src_local || !peer_base_host || !peer_flags_host || !epoch_dev) return EVOK_E_NULLPTR;
+  if (world < 1 || world > EVOK_MAX_PEERS || rank < 0 || rank >= world || n_bytes < 0 || dst_offset_bytes < 0 || (n_bytes & 3)) return EVOK_E_BADSIZE;
+  PeerSink sink{};
+  sink.world = world;
+  sink.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_base_host[p] || !peer_flags_host[p]) return EVOK_E_NULLPTR;
+    sink.data[p] = peer_base_host[p];
+    sink.flags[p] = static_cast<unsigned long long*>(peer_flags_host[p]);
+  }
+  peer_push_kernel<<<world, kPushThreads, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(src_local), n_bytes, dst_offset_bytes, sink,
+                                                                    reinterpret_cast<const unsigned long long*>(epoch_dev));
   EVOK_CHECK_LAUNCH();
   return 0;
 }

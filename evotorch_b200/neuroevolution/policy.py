@@ -5,7 +5,8 @@ A `Policy` wraps a torch module; `set_parameters(P)` takes either one flat param
 (one row per solution of the population), and `policy(obs)` then applies row i of P to row i of `obs`.  The reference does
 this with `vmap(functional_call)` (vecrl.py:1264).  Here, feed-forward nets made of `Linear` layers and Tanh / ReLU /
 Sigmoid / Identity activations run on the K8 kernel (csrc/evok_mlp.cu) for CUDA float32 tensors: every parameter row is read
-from HBM exactly once.  Any other module (recurrent nets, custom layers) or device takes the generic torch.func path.
+from HBM exactly once.  Any other stateless module (custom layers) or device takes the generic torch.func path; stateful
+(recurrent) modules are rejected, because the per-environment hidden-state handling of the reference is not implemented.
 """
 
 from __future__ import annotations
@@ -82,6 +83,11 @@ class Policy:
     """A (batch of) policies sharing one network architecture, parameterised by flat vectors (vecrl.py:1019)."""
 
     def __init__(self, net: nn.Module):
+        for m in net.modules():
+            if isinstance(m, (nn.RNNBase, nn.RNNCellBase)):
+                # the reference's Policy carries hidden states across calls and resets them per environment (vecrl.py:1160-1238);
+                # that state handling is not implemented here, and silently running a recurrent net without it would be wrong
+                raise NotImplementedError(f"Policy does not support stateful (recurrent) modules: found {type(m).__name__}")
         self._net = net
         self._names = [name for name, _ in net.named_parameters()]
         self._shapes = [p.shape for _, p in net.named_parameters()]

@@ -112,6 +112,16 @@ class PeerExchange:
     def _counter(self, i: int) -> int:
         return self._counters.data_ptr() + 4 * i
 
+    def push_fitness(self, row0: int, n_local: int) -> None:
+        """Copy this rank's fitness slice f_all[row0 : row0 + n_local] (already written locally by the sampler) into every peer's
+        `f_all` and raise this rank's flag there (one CTA per peer).  Follow with `wait_fitness()`."""
+        from . import ops
+
+        with ops._timed("peer_push"):
+            rc = nat.lib().evok_peer_push(self._base + self._off_f + 4 * row0, 4 * n_local, 4 * row0, self.world, self.rank, self.peer_f,
+                                          self.peer_flags_f, self.epoch_f, nat.stream_of(self.f_all))
+        nat.check(rc, "evok_peer_push")
+
     def wait_fitness(self) -> torch.Tensor:
         """Block the stream until every rank's fitness slice has landed in the local `f_all`."""
         from . import ops

@@ -336,6 +336,11 @@ int evok_sample_eval_push(int objective, float* X, int64_t ldx, const float* mu,
                           int64_t D, int symmetric, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, int world,
                           int rank, void* const* peer_f_host, void* const* peer_flags_host, const uint64_t* epoch_dev, uint32_t* done_dev,
                           void* stream);
+/* evok_peer_push: the all-gather as ONE small kernel behind the producer: CTA p copies this rank's slice (n_bytes at src_local) to
+ * offset dst_offset_bytes of peer p's buffer (peer_base_host[p]) with 16-byte stores, fences once and raises flag[rank] = *epoch_dev + 1
+ * on that peer.  Consumer: evok_peer_wait, as for evok_sample_eval_push. */
+int evok_peer_push(const void* src_local, int64_t n_bytes, int64_t dst_offset_bytes, int world, int rank, void* const* peer_base_host,
+                   void* const* peer_flags_host, const uint64_t* epoch_dev, void* stream);
 int evok_peer_wait(const uint64_t* flags_local, int world, uint64_t* epoch_dev, uint32_t* err_dev, uint64_t timeout_ns, void* stream);
 int evok_grad_push(int form, const float* X, int64_t ldx, const float* w, const float* mu, const float* sigma, int64_t row0,
                    int64_t n_rows, int64_t D, uint64_t seed, uint64_t stream_id, const uint32_t* stream_offset_dev, float scale_mu,
