@@ -495,57 +495,31 @@ struct ShardTable {
   long long off[EVOK_MAX_PEERS + 1];  // row offsets of the shards; off[world] = N
 };
 
-__global__ void __launch_bounds__(256)
+// One CTA per destination GPU (like evok_peer_push): CTA j copies ALL sorted keys of this rank into peer p's table with 16-byte
+// stores, adds up the local fitnesses (every CTA computes the same deterministic sum: fixed strided order + fixed tree), stores it,
+// fences ONCE and raises the flag on that peer.  No cross-CTA coordination, 8 system fences instead of one per CTA of a wide grid.
+constexpr int kRankPushThreads = 1024;
+
+__global__ void __launch_bounds__(kRankPushThreads)
     rank_push_kernel(const uint32_t* __restrict__ sorted_keys, const float* __restrict__ f, int64_t n_local, int64_t my_off,
-                     const __grid_constant__ PeerSink keys_sink, const __grid_constant__ PeerSink fsum_sink, const unsigned long long* epoch,
-                     unsigned int* done, double* partials /* gridDim.x doubles of local scratch */) {
+                     const __grid_constant__ PeerSink keys_sink, const __grid_constant__ PeerSink fsum_sink, const unsigned long long* epoch) {
   __shared__ double red[33];
-  __shared__ bool last;
-  const int world = keys_sink.world;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
-  // sorted keys -> every peer's table, 16 bytes per store where the shard offset allows (4x fewer NVLink transactions); the peers
-  // are visited in rotated order so that the GPUs do not all hit the same link at the same time
-  if ((my_off & 3) == 0) {
+  const int p = (keys_sink.rank + 1 + blockIdx.x) % keys_sink.world;  // rotated start: spread the links
+  uint32_t* dst = static_cast<uint32_t*>(keys_sink.data[p]) + my_off;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sorted_keys)) & 15u) == 0) {
     const int64_t nq = n_local >> 2;
-    for (int64_t q = gtid; q < nq; q += gsz) {
-      const uint4 k = reinterpret_cast<const uint4*>(sorted_keys)[q];
-      for (int j = 0; j < world; ++j) {
-        const int p = (keys_sink.rank + 1 + j) % world;
-        reinterpret_cast<uint4*>(static_cast<uint32_t*>(keys_sink.data[p]) + my_off)[q] = k;
-      }
-    }
-    for (int64_t i = (nq << 2) + gtid; i < n_local; i += gsz) {
-      const uint32_t k = sorted_keys[i];
-      for (int p = 0; p < world; ++p) static_cast<uint32_t*>(keys_sink.data[p])[my_off + i] = k;
-    }
+    for (int64_t q = threadIdx.x; q < nq; q += kRankPushThreads) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(sorted_keys)[q];
+    for (int64_t i = (nq << 2) + threadIdx.x; i < n_local; i += kRankPushThreads) dst[i] = sorted_keys[i];
   } else {
-    for (int64_t i = gtid; i < n_local; i += gsz) {
-      const uint32_t k = sorted_keys[i];
-      for (int p = 0; p < world; ++p) static_cast<uint32_t*>(keys_sink.data[p])[my_off + i] = k;
-    }
+    for (int64_t i = threadIdx.x; i < n_local; i += kRankPushThreads) dst[i] = sorted_keys[i];
   }
-  // deterministic local fitness sum (for the global mean_eval): per-CTA partial over a fixed element set, then the LAST CTA adds the
-  // partials in CTA order and pushes the total -- the same bits whatever the CTA scheduling was
   double acc = 0.0;
-  for (int64_t i = gtid; i < n_local; i += gsz) acc += (double)f[i];
-  const double part = block_sum<double>(acc, red);
+  for (int64_t i = threadIdx.x; i < n_local; i += kRankPushThreads) acc += (double)f[i];
+  const double tot = block_sum<double>(acc, red);
   if (threadIdx.x == 0) {
-    partials[blockIdx.x] = part;
-    __threadfence_system();  // this CTA's peer stores and its partial are visible before the counter moves
-    last = atomicAdd(done, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  double tot = 0.0;
-  for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) tot += __ldcg(partials + c);
-  tot = block_sum<double>(tot, red);
-  if (threadIdx.x == 0) {
-    for (int p = 0; p < world; ++p) static_cast<double*>(fsum_sink.data[p])[keys_sink.rank] = tot;
-    *done = 0;
+    static_cast<double*>(fsum_sink.data[p])[keys_sink.rank] = tot;
     __threadfence_system();
-    const unsigned long long e = *epoch + 1ull;
-    for (int p = 0; p < world; ++p) st_release_sys(keys_sink.flags[p] + keys_sink.rank, e);
+    st_release_sys(keys_sink.flags[p] + keys_sink.rank, *epoch + 1ull);
   }
 }
 
@@ -752,11 +726,7 @@ extern "C" EVOK_API int evok_rank_sharded(int method, const float* f_local, int6
     int rc = sort_pairs(f_local, n_local, !higher_is_better, ws, p, st, &sidx, &skeys);
     if (rc) return rc;
   }
-  int push_grid = (int)((n_local + 255) / 256);
-  if (push_grid > 2 * kNumSMs) push_grid = 2 * kNumSMs;
-  if (push_grid < 1) push_grid = 1;  // an empty shard still raises its flag
-  double* partials = reinterpret_cast<double*>((char*)ws + p.off_scalar + 64);  // 2 * kNumSMs doubles after the scalar slot
-  rank_push_kernel<<<push_grid, 256, 0, st>>>(skeys, f_local, n_local, my_off, keys_sink, fsum_sink, epoch, done_dev + 1, partials);
+  rank_push_kernel<<<world, kRankPushThreads, 0, st>>>(skeys, f_local, n_local, my_off, keys_sink, fsum_sink, epoch);
   EVOK_CHECK_LAUNCH();
   float* scalar = (float*)((char*)ws + p.off_scalar);
   if (method == EVOK_RANK_NES) {
