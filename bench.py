@@ -169,12 +169,15 @@ def cpu_reference_run(args, *, sizes, budget_s: float, max_steps: int, with_gpu_
             torch.cuda.empty_cache()
         except Exception as exc:  # e.g. out of memory for the temporaries: report, do not fail the bench
             torch_eager_gpu = {"unavailable": repr(exc)[:200]}
+    direct = next((r for r in per_size if r["popsize"] == 100_000 and args.dim == 10_000), None)
     return {
         "value": 1.0 / t_full,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
         "extrapolated": True,
+        # BASELINE config 2 (PGPE 100 k x 10 k) is one of the sampled sizes: measured directly, nothing extrapolated
+        "cfg2_direct": None if direct is None else {"generations_per_s": 1.0 / direct["median_s"], "median_s": direct["median_s"], "min_s": direct["min_s"]},
         "linearity": linearity,
         "samples": per_size,
         "torch_eager_gpu": torch_eager_gpu,

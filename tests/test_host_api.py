@@ -617,3 +617,28 @@ def test_adaptive_population_size_follows_the_reference_loop():
     assert out["num_solutions"] == 40 and set(out["gradients"]) == {"mu", "sigma"}
     out = prob2.sample_and_compute_gradients(dist, 10, num_interactions=100, popsize_max=30, ranking_method="centered")[0]
     assert out["num_solutions"] == 30
+
+
+def test_local_weight_conditions_and_policy_guards():
+    """Sharded ranking is only legal when a shard's gradient needs nothing but its own rows' utilities; Policy rejects stateful nets."""
+    from evotorch_b200.distributions import ExpSeparableGaussian, SeparableGaussian
+    from evotorch_b200.neuroevolution import Policy
+
+    mu, sg = torch.zeros(4), torch.ones(4)
+    sym = SymmetricSeparableGaussian({"mu": mu, "sigma": sg, "divide_mu_grad_by": "num_directions", "divide_sigma_grad_by": "num_directions"})
+    assert sym.accepts_local_weights("centered") and not sym.accepts_local_weights("nes") and not sym.accepts_local_weights("raw")
+    assert not SeparableGaussian({"mu": mu, "sigma": sg, "divide_mu_grad_by": "total_weight"}).accepts_local_weights("centered")
+    assert not SeparableGaussian({"mu": mu, "sigma": sg, "parenthood_ratio": 0.5}).accepts_local_weights("centered")
+    exp = ExpSeparableGaussian({"mu": mu, "sigma": sg})
+    assert exp.accepts_local_weights("nes") and not exp.accepts_local_weights("centered")
+    # gradients from a shard's own utilities == the slice-based partial gradients
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(12, 4, generator=g)
+    w = torch.randn(12, generator=g)
+    a = sym.partial_gradients(X[4:8], w, 4, "centered")
+    b = sym.partial_gradients(X[4:8], w[4:8].clone(), 4, "centered", local_weights_of=12)
+    assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["sigma"], b["sigma"])
+    with pytest.raises(ValueError):
+        sym.partial_gradients(X[4:8], w[4:8].clone(), 4, "nes", local_weights_of=12)
+    with pytest.raises(NotImplementedError):
+        Policy(torch.nn.Sequential(torch.nn.LSTM(3, 4)))
