@@ -242,4 +242,26 @@ struct ObjAcc<EVOK_OBJ_ACKLEY> {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// activations of the policy-forward kernels (tanh to ~1e-6 absolute: a 4-term odd polynomial below 0.25, (1 - e) / (1 + e) above)
+__device__ __forceinline__ float tanh_1e6(float x) {
+  const float ax = fabsf(x);
+  float r;
+  if (ax < 0.25f) {
+    const float t = ax * ax;
+    r = ax * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.021869488f, -0.053968254f), 0.13333334f), -0.33333334f), 1.0f);
+  } else {
+    const float e = __expf(-2.0f * ax);
+    r = __fdividef(1.0f - e, 1.0f + e);
+  }
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float activate_fast(float v, int act) {
+  switch (act) {
+    case EVOK_ACT_TANH: return tanh_1e6(v);
+    case EVOK_ACT_RELU: return fmaxf(v, 0.0f);
+    case EVOK_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-v));
+    default: return v;
+  }
+}
+
 }  // namespace evok

@@ -98,6 +98,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor of a K-major tile stored as rows of 128 bytes with the 128-byte swizzle
 // (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version(1)<<46 | layout(SWIZZLE_128B = 2)<<61)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -408,6 +418,246 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
+// ---- persistent gather GEMM (batched policy forward on ONE shared minibatch) ------------------------------------------------
+// Same arithmetic as gemm_tf32x3_kernel<true, true>, restructured for the shape this path has -- millions of A rows (the stacked
+// first-layer weights), a small B operand (the minibatch) that every tile re-reads:
+//   * PERSISTENT: one CTA per SM walks the output tiles (tile = blockIdx.x + q * gridDim.x), so barrier set-up and the TMEM allocation
+//     happen once, and the epilogue of tile q (bias, activation, 128 KB of stores) runs while the tensor core is already two
+//     accumulator chunks into tile q + 1 (the two TMEM accumulators of the chunked accumulation double as the overlap buffer);
+//   * the minibatch is split into hi / lo ONCE by a pre-pass (it is a few hundred KB) and both tiles arrive by TMA: the converter
+//     warps only derive the lo tile of the gathered A operand (a third of the element-wise work of the generic kernel);
+//   * the A ring (3 stages of raw + lo, 96 KB) is deeper than the B ring (2 stages of hi + lo, 128 KB): the gathered rows come from
+//     HBM (two 16 KB tiles in flight per SM), the minibatch tiles from L2;
+//   * the epilogue warps store their rows straight from registers (a row of the tile = 128 consecutive floats per thread).
+constexpr int kPersAStages = 3, kPersBStages = 2;
+constexpr uint32_t kPersAStageBytes = 2 * kTileABytes, kPersBStageBytes = 2 * kTileBBytes;
+constexpr size_t kPersSmemBytes = (size_t)kPersAStages * kPersAStageBytes + (size_t)kPersBStages * kPersBStageBytes + 1024 /*align*/ + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_gather_persistent_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+  extern __shared__ unsigned char gemm_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_base = base;
+  unsigned char* b_base = base + (size_t)kPersAStages * kPersAStageBytes;
+  uint64_t* full_b = reinterpret_cast<uint64_t*>(b_base + (size_t)kPersBStages * kPersBStageBytes);
+  uint64_t* empty_b = full_b + kPersBStages;
+  uint64_t* empty_a = empty_b + kPersBStages;
+  uint64_t* conv_a = empty_a + kPersAStages;
+  uint64_t* tmem_full = conv_a + kPersAStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int num_chunks = (num_kb + kGemmChunk - 1) / kGemmChunk;
+  const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
+  const int64_t total_tiles = (int64_t)((p.M + kGemmBM - 1) / kGemmBM) * n_tiles;
+  const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPersBStages; ++s) {
+      bar_init(&full_b[s], 1);
+      bar_init(&empty_b[s], 1);
+    }
+    for (int s = 0; s < kPersAStages; ++s) {
+      bar_init(&empty_a[s], 1);
+      bar_init(&conv_a[s], 2);  // one arrival per converter warp
+    }
+    for (int t = 0; t < 2; ++t) {
+      bar_init(&tmem_full[t], 1);
+      bar_init(&tmem_empty[t], 8);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kGemmBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer of the minibatch tiles (hi, lo) =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int64_t q = 0; q < my_tiles; ++q) {
+        const int64_t t = blockIdx.x + q * gridDim.x;
+        const int n0 = (int)(t % n_tiles) * kGemmBN;
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % kPersBStages;
+          bar_wait(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);
+          unsigned char* st = b_base + (size_t)s * kPersBStageBytes;
+          bar_expect_tx(&full_b[s], kPersBStageBytes);
+          tma_load_2d(st, &map_b_hi, i * kGemmBK, n0, &full_b[s]);
+          tma_load_2d(st + kTileBBytes, &map_b_lo, i * kGemmBK, n0, &full_b[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue =====
+    if (lane == 0) {
+      uint32_t g = 0, gch = 0;
+      for (int64_t q = 0; q < my_tiles; ++q) {
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int sa = g % kPersAStages, sb = g % kPersBStages;
+          const int in_chunk = i % kGemmChunk;
+          const int buf = gch & 1;
+          if (in_chunk == 0 && gch >= 2) {  // the epilogue must have folded the chunk that used this accumulator (two chunks ago)
+            bar_wait(&tmem_empty[buf], ((gch >> 1) - 1) & 1);
+            tc_fence_after();
+          }
+          bar_wait(&conv_a[sa], (g / kPersAStages) & 1);
+          bar_wait(&full_b[sb], (g / kPersBStages) & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)(buf * kGemmBN);
+          const uint32_t sta = s32(a_base + (size_t)sa * kPersAStageBytes), stb = s32(b_base + (size_t)sb * kPersBStageBytes);
+          const uint64_t a_hi = make_sw128_desc(sta), a_lo = make_sw128_desc(sta + kTileABytes);
+          const uint64_t b_hi = make_sw128_desc(stb), b_lo = make_sw128_desc(stb + kTileBBytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / kUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);
+            umma_tf32(acc, a_hi + adv, b_lo + adv, kIdesc, (in_chunk | k) != 0);
+            umma_tf32(acc, a_lo + adv, b_hi + adv, kIdesc, 1);
+            umma_tf32(acc, a_hi + adv, b_hi + adv, kIdesc, 1);
+          }
+          umma_commit(&empty_a[sa]);
+          umma_commit(&empty_b[sb]);
+          if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) {
+            umma_commit(&tmem_full[buf]);
+            ++gch;
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===== 2 converter warps: gather the A tile of K-block g (4-byte cp.async, 64 rows per warp), derive its lo tile =====
+    const int ct = threadIdx.x - 64;
+    const uint32_t total_g = (uint32_t)(my_tiles * num_kb);
+    auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+    auto issue_gather = [&](uint32_t g) {
+      const int s = g % kPersAStages;
+      bar_wait(&empty_a[s], ((g / kPersAStages) & 1) ^ 1);
+      const int64_t q = g / num_kb;
+      const int i = (int)(g - q * num_kb);
+      const int64_t t = blockIdx.x + q * gridDim.x;
+      const int m0 = (int)(t / n_tiles) * kGemmBM;
+      const uint32_t st_a = s32(a_base + (size_t)s * kPersAStageBytes);
+      const int kcol = i * kGemmBK + lane;
+      const bool k_ok = kcol < p.K;
+      const int wrow0 = (warp - 2) * 64;
+      const int m_first = m0 + wrow0;
+      int hrow = m_first % (int)p.ga_rows_per_batch;
+      const float* rowp = p.gather_a + (int64_t)(m_first / (int)p.ga_rows_per_batch) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
+      const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
+#pragma unroll 8
+      for (int it = 0; it < 64; ++it) {
+        const int r = wrow0 + it;
+        const bool ok = k_ok && (m0 + r < p.M);
+        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+        const float* src = ok ? rowp : p.gather_a;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st_a + off), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        rowp += p.ga_row_stride;
+        if (++hrow == (int)p.ga_rows_per_batch) {
+          hrow = 0;
+          rowp += wrap;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (total_g > 0) issue_gather(0);
+    if (total_g > 1) issue_gather(1);
+    for (uint32_t g = 0; g < total_g; ++g) {
+      const int s = g % kPersAStages;
+      if (g + 1 < total_g) asm volatile("cp.async.wait_group 1;" ::: "memory");  // block g has landed (block g + 1 may be in flight)
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 64;" ::: "memory");  // ... and so have the other converter warp's rows
+      unsigned char* st = a_base + (size_t)s * kPersAStageBytes;
+      const float4* a_raw = reinterpret_cast<const float4*>(st);
+      float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
+#pragma unroll 4
+      for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
+        const float4 v = a_raw[ct + 64 * j];
+        a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv_a[s])) : "memory");
+      if (g + 2 < total_g) issue_gather(g + 2);
+    }
+  } else {
+    // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4 (tile row = quadrant * 32 + lane), column half = (warp - 4) / 4 =====
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+    uint32_t gch = 0;
+    for (int64_t q = 0; q < my_tiles; ++q) {
+      const int64_t t = blockIdx.x + q * gridDim.x;
+      const int m0 = (int)(t / n_tiles) * kGemmBM, n0 = (int)(t % n_tiles) * kGemmBN;
+      float acc[kGemmBN / 2];
+#pragma unroll
+      for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
+      for (int ch = 0; ch < num_chunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        bar_wait(&tmem_full[buf], (gch >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kGemmBN + half * (kGemmBN / 2) + g8 * 16), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[g8 * 16 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
+      }
+      const int64_t m = (int64_t)m0 + quad * 32 + lane;
+      if (m < p.M) {
+        float b = 0.0f;
+        if (p.row_bias) {
+          const int64_t bi = m / p.ga_rows_per_batch;
+          b = __ldg(p.row_bias + bi * p.rb_batch_stride + (m - bi * p.ga_rows_per_batch));
+        }
+        // bias + activation applied four values at a time on the way out; one unrolled copy of the store loop per activation (a
+        // per-element switch would not fit the instruction cache)
+        float* crow = p.C + m * p.ldc;
+        const int col0 = n0 + half * (kGemmBN / 2);
+        auto store4 = [&](int j, float v0, float v1, float v2, float v3) {
+          const int col = col0 + j;
+          if (vec_ok && col + 4 <= p.N) {
+            *reinterpret_cast<float4*>(crow + col) = make_float4(v0, v1, v2, v3);
+          } else {
+            const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (col + u < p.N) crow[col + u] = v[u];
+          }
+        };
+        if (p.row_act == EVOK_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; j += 4) store4(j, acc[j] + b, acc[j + 1] + b, acc[j + 2] + b, acc[j + 3] + b);
+        } else if (p.row_act == EVOK_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; j += 4)
+            store4(j, fmaxf(acc[j] + b, 0.0f), fmaxf(acc[j + 1] + b, 0.0f), fmaxf(acc[j + 2] + b, 0.0f), fmaxf(acc[j + 3] + b, 0.0f));
+        } else if (p.row_act == EVOK_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; j += 4)
+            store4(j, tanh_1e6(acc[j] + b), tanh_1e6(acc[j + 1] + b), tanh_1e6(acc[j + 2] + b), tanh_1e6(acc[j + 3] + b));
+        } else {
+#pragma unroll
+          for (int j = 0; j < kGemmBN / 2; j += 4)
+            store4(j, activate_fast(acc[j] + b, EVOK_ACT_SIGMOID), activate_fast(acc[j + 1] + b, EVOK_ACT_SIGMOID),
+                   activate_fast(acc[j + 2] + b, EVOK_ACT_SIGMOID), activate_fast(acc[j + 3] + b, EVOK_ACT_SIGMOID));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kGemmBN);
+  }
+}
+
 // ---- operand preparation -----------------------------------------------------------------------------------------
 // hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols, float* __restrict__ hi,
@@ -682,6 +932,65 @@ extern "C" EVOK_API int evok_gemm_gather_rows(const float* params, int64_t batch
   }
   dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((n_cols + kGemmBN - 1) / kGemmBN), 1);
   gemm_tf32x3_kernel<true, true><<<grid, kGemmThreads, kGemmSmemBytes, (cudaStream_t)stream>>>(mb, mb, mb, mb, p);
+  EVOK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" EVOK_API size_t evok_gemm_gather_rows_workspace_bytes(int64_t n_cols, int64_t K) {
+  if (n_cols <= 0 || K <= 0) return 512;
+  return (size_t)2 * n_cols * round_up(K, 4) * sizeof(float) + 512;
+}
+
+// The same product on the persistent kernel (gemm_gather_persistent_kernel): X is split into hi / lo copies in `ws` first (any
+// alignment / pitch of X is fine).  EVOK_GATHER_PERSISTENT=0 routes to the one-tile-per-CTA kernel instead (measurement only).
+extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch,
+                                                 int64_t n_batches, const float* X, int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset,
+                                                 int act, float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  if (!params || !X || !C || !ws) return EVOK_E_NULLPTR;
+  const int64_t M = rows_per_batch * n_batches;
+  if (rows_per_batch <= 0 || n_batches <= 0 || n_cols <= 0 || K <= 0 || ldx < K || ldc < n_cols || M >= (1ll << 31)) return EVOK_E_BADSIZE;
+  if (act < EVOK_ACT_NONE || act > EVOK_ACT_SIGMOID) return EVOK_E_BADENUM;
+  {
+    const char* e = getenv("EVOK_GATHER_PERSISTENT");
+    if (e && atoi(e) == 0 && tma_ok(X, ldx))
+      return evok_gemm_gather_rows(params, batch_stride, w_offset, rows_per_batch, n_batches, X, ldx, n_cols, K, bias_offset, act, C, ldc, stream);
+  }
+  const int64_t ldk = round_up(K, 4);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)2 * n_cols * ldk * sizeof(float)) return EVOK_E_WORKSPACE;
+  float* x_hi = reinterpret_cast<float*>(base);
+  float* x_lo = x_hi + n_cols * ldk;
+  split_tf32_kernel<<<(unsigned)((n_cols * K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n_cols, K, x_hi, x_lo, ldk);
+  EVOK_CHECK_LAUNCH();
+  CUtensorMap mhi, mlo;
+  int rc;
+  if ((rc = make_map(&mhi, x_hi, n_cols, K, ldk, kGemmBN))) return rc;
+  if ((rc = make_map(&mlo, x_lo, n_cols, K, ldk, kGemmBN))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)n_cols; p.K = (int)K;
+  p.kblocks_per_split = (int)((K + kGemmBK - 1) / kGemmBK);
+  p.C = C;
+  p.ldc = ldc;
+  p.gather_a = params + w_offset;
+  p.ga_rows_per_batch = rows_per_batch;
+  p.ga_batch_stride = batch_stride;
+  p.ga_row_stride = K;
+  p.row_bias = bias_offset >= 0 ? params + bias_offset : nullptr;
+  p.rb_batch_stride = batch_stride;
+  p.row_act = act;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    if (cudaFuncSetAttribute(gemm_gather_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersSmemBytes) != cudaSuccess) {
+      sm_count = 0;
+      return (int)cudaGetLastError();
+    }
+  }
+  const int64_t tiles = ((M + kGemmBM - 1) / kGemmBM) * ((n_cols + kGemmBN - 1) / kGemmBN);
+  const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
+  gemm_gather_persistent_kernel<<<grid, kGemmThreads, kPersSmemBytes, (cudaStream_t)stream>>>(mhi, mlo, p);
   EVOK_CHECK_LAUNCH();
   return 0;
 }

@@ -182,27 +182,6 @@ constexpr int kTailOutBlock = 4;  // outputs per thread per pass (register block
 
 // tanh to ~1e-6 absolute: odd polynomial near 0, (1 - e) / (1 + e) with e = exp(-2|x|) elsewhere.  The accurate tanhf costs ~50
 // instructions; 65 536 networks x 256 hidden units x 256 samples of them were a third of the forward.
-__device__ __forceinline__ float tanh_1e6(float x) {
-  const float ax = fabsf(x);
-  float r;
-  if (ax < 0.25f) {
-    const float t = ax * ax;
-    r = ax * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.021869488f, -0.053968254f), 0.13333334f), -0.33333334f), 1.0f);
-  } else {
-    const float e = __expf(-2.0f * ax);
-    r = __fdividef(1.0f - e, 1.0f + e);
-  }
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float activate_fast(float v, int act) {
-  switch (act) {
-    case EVOK_ACT_TANH: return tanh_1e6(v);
-    case EVOK_ACT_RELU: return fmaxf(v, 0.0f);
-    case EVOK_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-v));
-    default: return v;
-  }
-}
-
 // hid holds the first layer's PRE-activation (W_0 x + b_0); its activation is applied while the tile is loaded.
 __global__ void __launch_bounds__(kTailThreads)
     mlp_tail_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ hid, int64_t ldh, int64_t n_first, int64_t B,
@@ -266,46 +245,110 @@ __global__ void __launch_bounds__(kTailThreads)
 // in registers: per hidden unit one load, one activation and dout broadcast weight reads serving 2 x dout FMAs.
 constexpr int kTail2MaxOut = 32;
 
-template <int DOUT_MAX>
-__global__ void __launch_bounds__(kTailThreads)
+// The hidden tile of 64 samples (h1 x 64 floats) is brought into shared memory with 16-byte cp.async copies, all of them issued up
+// front in four commit groups (streaming the rows from inside the accumulation loop, or filling the tile with plain loads, was
+// latency-bound: 35 ms of a 74 ms forward); each thread applies act_0 in place to the pieces it copied as its group lands, and the
+// accumulation over a quarter of the hidden units starts while the other quarters are still in flight.  Thread = (sample pair,
+// output group): per hidden unit two activation reads and one or two 16-byte broadcast weight reads serve 2 x OG FMAs.  96 KB of
+// shared memory per CTA: two CTAs per SM cover each other's fill latency.
+constexpr int kTail2Threads = 128;
+constexpr int kTail2Samples = 64;   // samples per pass
+constexpr int kTail2Groups = 4;     // output groups (one warp each)
+constexpr int kTail2Slots = 8;      // padded outputs per group: weights of hidden unit h, group g at wsm[(h * 4 + g) * 8 ..]
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int OG>  // outputs per thread (dout <= 4 * OG)
+__global__ void __launch_bounds__(kTail2Threads)
     mlp_tail2_kernel(const float* __restrict__ params, int64_t ldp, const float* __restrict__ hid, int64_t ldh, int64_t n_first, int64_t B,
                      float* __restrict__ out, const __grid_constant__ MlpSpec spec) {
-  extern __shared__ float tail_smem[];
+  extern __shared__ __align__(16) float tail_smem[];
   const int64_t net = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int h1 = spec.dims[1], dout = spec.dims[2];
+  float* tile = tail_smem;                                                  // [h1][64]
+  float* wsm = tile + (size_t)h1 * kTail2Samples;                           // [h1][4][8]
+  float* bsm = wsm + (size_t)h1 * kTail2Groups * kTail2Slots;               // [32]
   const float* W = params + (net + n_first) * ldp + spec.w_off[1];
-  for (int e = threadIdx.x; e < h1 * dout + dout; e += kTailThreads) tail_smem[e] = __ldg(W + e);
+  for (int e = threadIdx.x; e < h1 * kTail2Groups * kTail2Slots; e += kTail2Threads) wsm[e] = 0.0f;
+  if (threadIdx.x < kTail2Groups * kTail2Slots) bsm[threadIdx.x] = 0.0f;
   __syncthreads();
-  const float* bias = tail_smem + (size_t)h1 * dout;
+  for (int e = threadIdx.x; e < h1 * dout; e += kTail2Threads) {
+    const int o = e / h1, h = e - o * h1;
+    wsm[(h * kTail2Groups + o / OG) * kTail2Slots + o % OG] = __ldg(W + e);
+  }
+  if (threadIdx.x < dout) bsm[(threadIdx.x / OG) * kTail2Slots + threadIdx.x % OG] = __ldg(W + h1 * dout + threadIdx.x);
   const float* hrow = hid + net * h1 * ldh;
-  for (int64_t b0 = (int64_t)wid * 64; b0 < B; b0 += (kTailThreads / 32) * 64) {
-    const int64_t ba = b0 + lane, bb = b0 + 32 + lane;
-    const bool oka = ba < B, okb = bb < B;
-    float acca[DOUT_MAX], accb[DOUT_MAX];
+  const int sp = threadIdx.x & 31, og = threadIdx.x >> 5;
+  const int hq = (h1 + 3) / 4;  // hidden units per commit group
+  for (int64_t b0 = 0; b0 < B; b0 += kTail2Samples) {
+    const int vec = (int)((ldh - b0 < kTail2Samples ? ldh - b0 : kTail2Samples) / 4);  // 16-byte pieces per row (ldh is a multiple of 4)
+    __syncthreads();  // weights staged / the previous pass is done with the tile
 #pragma unroll
-    for (int o = 0; o < DOUT_MAX; ++o) acca[o] = accb[o] = 0.0f;
-#pragma unroll 2
-    for (int h = 0; h < h1; ++h) {
-      const float xa = oka ? activate_fast(__ldg(hrow + (int64_t)h * ldh + ba), spec.acts[0]) : 0.0f;
-      const float xb = okb ? activate_fast(__ldg(hrow + (int64_t)h * ldh + bb), spec.acts[0]) : 0.0f;
+    for (int q = 0; q < 4; ++q) {
+      const int ha = q * hq, hb = (ha + hq < h1) ? ha + hq : h1;
+      for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
+        const int h = e >> 4, v = e & 15;
+        if (v < vec) cp_async_16(tile + h * kTail2Samples + v * 4, hrow + (int64_t)h * ldh + b0 + v * 4);
+      }
+      cp_async_commit();
+    }
+    float acca[OG], accb[OG];
 #pragma unroll
-      for (int o = 0; o < DOUT_MAX; ++o) {
-        if (o < dout) {
-          const float w = tail_smem[o * h1 + h];
-          acca[o] = fmaf(w, xa, acca[o]);
-          accb[o] = fmaf(w, xb, accb[o]);
+    for (int j = 0; j < OG; ++j) acca[j] = accb[j] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q == 0) cp_async_wait<3>();
+      else if (q == 1) cp_async_wait<2>();
+      else if (q == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      const int ha = q * hq, hb = (ha + hq < h1) ? ha + hq : h1;
+      // act_0 in place, on the pieces this thread copied (its own cp.async writes are visible to it after the wait)
+      for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
+        const int h = e >> 4, v = e & 15;
+        if (v < vec) {
+          float4* p4 = reinterpret_cast<float4*>(tile + h * kTail2Samples + v * 4);
+          float4 t = *p4;
+          t.x = activate_fast(t.x, spec.acts[0]);
+          t.y = activate_fast(t.y, spec.acts[0]);
+          t.z = activate_fast(t.z, spec.acts[0]);
+          t.w = activate_fast(t.w, spec.acts[0]);
+          *p4 = t;
+        }
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int h = ha; h < hb; ++h) {
+        const float xa = tile[h * kTail2Samples + sp], xb = tile[h * kTail2Samples + 32 + sp];
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots);
+        float w[8] = {w0.x, w0.y, w0.z, w0.w, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (OG > 4) {
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots + 4);
+          w[4] = w1.x, w[5] = w1.y, w[6] = w1.z, w[7] = w1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < OG; ++j) {
+          acca[j] = fmaf(w[j], xa, acca[j]);
+          accb[j] = fmaf(w[j], xb, accb[j]);
         }
       }
     }
+    const int64_t ba = b0 + sp, bb = b0 + 32 + sp;
 #pragma unroll
-    for (int o = 0; o < DOUT_MAX; ++o) {
+    for (int j = 0; j < OG; ++j) {
+      const int o = og * OG + j;
       if (o < dout) {
-        if (oka) out[(net * B + ba) * dout + o] = activate_fast(acca[o] + bias[o], spec.acts[1]);
-        if (okb) out[(net * B + bb) * dout + o] = activate_fast(accb[o] + bias[o], spec.acts[1]);
+        const float bias = bsm[og * kTail2Slots + j];
+        if (ba < B) out[(net * B + ba) * dout + o] = activate_fast(acca[j] + bias, spec.acts[1]);
+        if (bb < B) out[(net * B + bb) * dout + o] = activate_fast(accb[j] + bias, spec.acts[1]);
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace evok
@@ -319,7 +362,7 @@ extern "C" EVOK_API size_t evok_mlp_forward_shared_workspace_bytes(int64_t N, in
   if (chunk < 1) chunk = 1;
   if (chunk > 65535) chunk = 65535;
   if (chunk > N) chunk = N;
-  return (size_t)chunk * dims_host[1] * ldh * 4 + 256;
+  return (size_t)chunk * dims_host[1] * ldh * 4 + 256 + evok_gemm_gather_rows_workspace_bytes(B, dims_host[0]);
 }
 
 // out[i, b, :] = net_i(X[b, :]) for N flat parameter rows and ONE shared input batch X (B x dims[0], 16-byte aligned rows).
@@ -354,8 +397,15 @@ extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp
   if (chunk > 65535) chunk = 65535;  // gridDim.y of the tail kernel
   if (chunk > N) chunk = N;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)chunk * h1 * ldh * 4) return EVOK_E_WORKSPACE;
+  const size_t hid_bytes = ((size_t)chunk * h1 * ldh * 4 + 255) & ~(size_t)255;
+  const size_t gws_bytes = evok_gemm_gather_rows_workspace_bytes(B, spec.dims[0]);
+  if (ws_bytes < (size_t)(base - (char*)ws) + hid_bytes + gws_bytes) return EVOK_E_WORKSPACE;
   float* hid = reinterpret_cast<float*>(base);
+  void* gws = base + hid_bytes;
+  // act_0 is applied by the GEMM epilogue (its warps have slack while the tensor core works on the next tile): the tail kernels
+  // read activations
+  MlpSpec tail_spec = spec;
+  tail_spec.acts[0] = EVOK_ACT_NONE;
   size_t wmax = 0;  // largest staged layer (weights + bias) among the layers 1 .. n-1
   for (int l = 1; l < n_layers; ++l) {
     const size_t wl = (size_t)spec.dims[l] * spec.dims[l + 1] + spec.dims[l + 1];
@@ -371,24 +421,28 @@ extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t c = (N - i0) < chunk ? (N - i0) : chunk;
     // layer 0 of the c networks as ONE stacked-rows tensor-core product: (c * H1 x in) * (in x B)
-    int rc = evok_gemm_gather_rows(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0], spec.w_off[0] + (int64_t)spec.dims[0] * h1,
-                                   EVOK_ACT_NONE /* act_0 is applied by the tail kernel while it loads the tile */, hid, ldh, stream);
+    int rc = evok_gemm_gather_rows_ws(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0],
+                                      spec.w_off[0] + (int64_t)spec.dims[0] * h1, spec.acts[0], hid, ldh, gws, gws_bytes, stream);
     if (rc) return rc;
-    if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut) {
-      const size_t smem2 = ((size_t)h1 * spec.dims[2] + spec.dims[2]) * sizeof(float);
-      if (spec.dims[2] <= 8) {
-        cudaFuncSetAttribute(mlp_tail2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        mlp_tail2_kernel<8><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
-      } else if (spec.dims[2] <= 17) {
-        cudaFuncSetAttribute(mlp_tail2_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        mlp_tail2_kernel<17><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
-      } else {
-        cudaFuncSetAttribute(mlp_tail2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        mlp_tail2_kernel<32><<<(unsigned)c, kTailThreads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[2], spec);
-      }
+    const size_t smem2 = ((size_t)h1 * kTail2Samples + (size_t)h1 * kTail2Groups * kTail2Slots + kTail2Groups * kTail2Slots) * sizeof(float);
+    if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut && smem2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(hid) & 15) == 0) {
+      // 4 output groups (one warp each) x 32 sample pairs = 128 threads; outputs per thread = ceil(dout / 4)
+      const int og = (spec.dims[2] + kTail2Groups - 1) / kTail2Groups;
+#define EVOK_LAUNCH_TAIL2(OGV)                                                                                                      \
+  do {                                                                                                                              \
+    cudaFuncSetAttribute(mlp_tail2_kernel<OGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);                           \
+    mlp_tail2_kernel<OGV><<<(unsigned)c, kTail2Threads, smem2, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B,                \
+                                                                                       out + i0 * B * spec.dims[2], tail_spec);      \
+  } while (0)
+      if (og <= 1) EVOK_LAUNCH_TAIL2(1);
+      else if (og <= 2) EVOK_LAUNCH_TAIL2(2);
+      else if (og <= 4) EVOK_LAUNCH_TAIL2(4);
+      else if (og <= 5) EVOK_LAUNCH_TAIL2(5);
+      else EVOK_LAUNCH_TAIL2(8);
+#undef EVOK_LAUNCH_TAIL2
     } else {
       dim3 grid((unsigned)((B + kTailSamples - 1) / kTailSamples), (unsigned)c);
-      mlp_tail_kernel<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[n_layers], spec);
+      mlp_tail_kernel<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(params, ldp, hid, ldh, i0, B, out + i0 * B * spec.dims[n_layers], tail_spec);
     }
     EVOK_CHECK_LAUNCH();
   }
