@@ -162,10 +162,23 @@ class private_workspaces:
         self._saved = _workspaces
         _workspaces = self.store = {}
         _private_depth += 1
+        # The cyclic garbage collector is held off for the duration of the capture: a collection that finalises an object owning
+        # CUDA resources (a peer-exchange buffer with its IPC handles, an event) calls cudaFree / cudaIpcCloseMemHandle, which is
+        # prohibited while a stream of the process is capturing and invalidates the capture ("operation failed due to a previous
+        # error during capture" from the next launch -- seen once in the full GPU suite, never in the test alone).
+        import gc
+
+        self._gc_was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()
         return self.store
 
     def __exit__(self, *exc):
         global _workspaces, _private_depth
         _workspaces = self._saved
         _private_depth -= 1
+        if self._gc_was_enabled:
+            import gc
+
+            gc.enable()
         return False

@@ -57,6 +57,26 @@ __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(s32(b)), "r"(parity) : "memory");
 }
+// The same wait for warps that are NOT on the critical path (the epilogue warps waiting for an accumulator chunk, the TMA producer
+// waiting for a free stage): sleep between polls.  A tight try_wait loop issues continuously, and eight spinning epilogue warps share
+// the four schedulers with the two converter warps -- ncu showed the converters issue-starved at 0.13 IPC while the spin loops
+// executed more instructions than the rest of the kernel.
+__device__ __forceinline__ void bar_wait_relaxed(uint64_t* b, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
                "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(s32(bar))
@@ -122,6 +142,27 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 256
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
 
+// lo = x - trunc_tf32(x) of a whole tile, by 64 threads: thread ct handles the float4 at byte ct * 16 + j * 1024 (addresses in the shared
+// window); 16 loads are issued before the first use
+template <uint32_t BYTES>
+__device__ __forceinline__ void split_lo_tile(uint32_t src, uint32_t dst) {
+#pragma unroll
+  for (uint32_t b = 0; b < BYTES / 1024u; b += 16) {
+    float4 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "r"(src + (b + j) * 1024u));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float lx = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+      const float ly = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+      const float lz = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+      const float lw = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (b + j) * 1024u), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+    }
+  }
+}
+
 struct GemmParams {
   int M, N, K;
   int kblocks_per_split;
@@ -147,6 +188,7 @@ struct GemmParams {
   int64_t rb_batch_stride;
   int row_act;
   int debug;  // measurement only (EVOK_GATHER_DEBUG): 1 = skip the global loads of the gather, 2 = skip bias / activation
+  int b_lo_tma;  // CONVERT: the lo tile of B comes from a pre-split copy (map_b_lo) instead of being derived by the converter warps
 };
 
 // The tensor core adds every MMA into the TMEM accumulator with round-toward-zero; over hundreds of MMAs that is a
@@ -212,14 +254,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kGemmStages;
         const uint32_t use = i / kGemmStages;
-        bar_wait(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
+        bar_wait_relaxed(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
         unsigned char* st = base + (size_t)s * kStageBytes;
-        bar_expect_tx(&full[s], GATHER ? kTileBBytes : (CONVERT ? kTileABytes + kTileBBytes : kStageBytes));
+        bar_expect_tx(&full[s], (GATHER ? kTileBBytes : (CONVERT ? kTileABytes + kTileBBytes : kStageBytes)) + ((CONVERT && p.b_lo_tma) ? kTileBBytes : 0u));
         const int kx = (kb_begin + i) * kGemmBK;
         if (!GATHER) tma_load_2d(st, &map_a_hi, kx, m0, &full[s]);
         if (!CONVERT) tma_load_2d(st + kTileABytes, &map_a_lo, kx, m0, &full[s]);
         tma_load_2d(st + 2 * kTileABytes, &map_b_hi, kx, n0, &full[s]);
-        if (!CONVERT) tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
+        if (!CONVERT || p.b_lo_tma) tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, kx, n0, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -303,16 +345,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
         const float4* b_raw = reinterpret_cast<const float4*>(st + 2 * kTileABytes);
         float4* b_lo = reinterpret_cast<float4*>(st + 2 * kTileABytes + kTileBBytes);
-#pragma unroll 4
-        for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
-          const float4 v = a_raw[ct + 64 * j];
-          a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
-        }
-#pragma unroll 4
-        for (int j = 0; j < (int)(kTileBBytes / 16 / 64); ++j) {
-          const float4 v = b_raw[ct + 64 * j];
-          b_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
-        }
+        // (a single warp runs this dependent stream at ~0.2 IPC, so the instruction count per K-block is what matters: shared-space
+        // 16-byte loads / stores with immediate offsets, 16 loads in flight; B is skipped when its lo tile came by TMA)
+        split_lo_tile<kTileABytes>(s32(a_raw) + (uint32_t)ct * 16u, s32(a_lo) + (uint32_t)ct * 16u);
+        if (!p.b_lo_tma) split_lo_tile<kTileBBytes>(s32(b_raw) + (uint32_t)ct * 16u, s32(b_lo) + (uint32_t)ct * 16u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv[s])) : "memory");
@@ -332,7 +368,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
     auto fold_chunk = [&](int ch) {
       const int buf = ch & 1;
-      bar_wait(&tmem_full[buf], (ch >> 1) & 1);
+      bar_wait_relaxed(&tmem_full[buf], (ch >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -426,32 +462,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 //     accumulator chunks into tile q + 1 (the two TMEM accumulators of the chunked accumulation double as the overlap buffer);
 //   * the minibatch is split into hi / lo ONCE by a pre-pass (it is a few hundred KB) and both tiles arrive by TMA: the converter
 //     warps only derive the lo tile of the gathered A operand (a third of the element-wise work of the generic kernel);
-//   * the A ring (3 stages of raw + lo, 96 KB) is deeper than the B ring (2 stages of hi + lo, 128 KB): the gathered rows come from
-//     HBM (two 16 KB tiles in flight per SM), the minibatch tiles from L2;
+//   * the gathered A tiles live in a 4-deep ring of raw tiles (three 16 KB gathers in flight per SM while one is converted) with only
+//     two lo buffers behind it (a lo tile is derived right before its MMAs); the minibatch tiles (2 stages of hi + lo, 128 KB) come
+//     from L2;
 //   * the epilogue warps store their rows straight from registers (a row of the tile = 128 consecutive floats per thread).
-constexpr int kPersAStages = 3, kPersBStages = 2;
-constexpr uint32_t kPersAStageBytes = 2 * kTileABytes, kPersBStageBytes = 2 * kTileBBytes;
-constexpr size_t kPersSmemBytes = (size_t)kPersAStages * kPersAStageBytes + (size_t)kPersBStages * kPersBStageBytes + 1024 /*align*/ + 256;
+// the minibatch operand, pre-split into hi / lo and stored four times, copy s shifted right by s floats (xs[b][k'] = x[b][k' - s], zero
+// outside): TMA needs 16-byte aligned box coordinates (an odd K coordinate is an illegal instruction), so a tile whose rows sit sh
+// floats past a 16-byte boundary reads copy sh at the aligned coordinate 32 i instead of the original at 32 i - sh
+struct GatherMaps {
+  CUtensorMap hi[4];
+  CUtensorMap lo[4];
+};
+
+constexpr int kPersRawStages = 4, kPersLoStages = 2, kPersBStages = 2;
+constexpr uint32_t kPersBStageBytes = 2 * kTileBBytes;
+constexpr size_t kPersSmemBytes =
+    (size_t)(kPersRawStages + kPersLoStages) * kTileABytes + (size_t)kPersBStages * kPersBStageBytes + 1024 /*align*/ + 256;
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_gather_persistent_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+    gemm_gather_persistent_kernel(const __grid_constant__ GatherMaps maps, const GemmParams p) {
   extern __shared__ unsigned char gemm_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* a_base = base;
-  unsigned char* b_base = base + (size_t)kPersAStages * kPersAStageBytes;
+  unsigned char* raw_base = base;                                             // gathered A tiles (= the hi operand)
+  unsigned char* lo_base = base + (size_t)kPersRawStages * kTileABytes;       // their lo tiles
+  unsigned char* b_base = lo_base + (size_t)kPersLoStages * kTileABytes;
   uint64_t* full_b = reinterpret_cast<uint64_t*>(b_base + (size_t)kPersBStages * kPersBStageBytes);
   uint64_t* empty_b = full_b + kPersBStages;
-  uint64_t* empty_a = empty_b + kPersBStages;
-  uint64_t* conv_a = empty_a + kPersAStages;
-  uint64_t* tmem_full = conv_a + kPersAStages;  // [2]
+  uint64_t* empty_raw = empty_b + kPersBStages;
+  uint64_t* empty_lo = empty_raw + kPersRawStages;
+  uint64_t* conv_a = empty_lo + kPersLoStages;
+  uint64_t* tmem_full = conv_a + kPersLoStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  // VECTOR mode (rows of K % 4 == 0 floats at pitch K, a tile never straddles two batches): all rows of a tile share one misalignment
+  // `sh` (0..3 floats past a 16-byte boundary), so the K axis of that tile is simply cut at 16-byte-aligned source addresses --
+  // K-block i covers k = 32 i - sh .. 32 i - sh + 31 for BOTH operands (the minibatch tile comes from the copy shifted by sh floats,
+  // GatherMaps; zeros for k < 0 and k >= K) -- and the gather moves 16 bytes per copy.  4-byte cp.async copies turned out to cost ~57 issue
+  // cycles per warp instruction (ncu: 70 % of the converter warps' samples sat on the 64 LDGSTS of a K-block), which bounded the
+  // whole kernel at 2.6 us per K-block against 0.9 us of tensor-core work.
+  const bool vec_mode = (p.K % 4 == 0) && (p.ga_row_stride == p.K) && (p.ga_rows_per_batch % kGemmBM == 0);
+  const int num_kb = (p.K + (vec_mode ? 3 : 0) + kGemmBK - 1) / kGemmBK;
   const int num_chunks = (num_kb + kGemmChunk - 1) / kGemmChunk;
   const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
   const int64_t total_tiles = (int64_t)((p.M + kGemmBM - 1) / kGemmBM) * n_tiles;
+  auto tile_rows = [&](int64_t t, int& m0, int& sh) -> const float* {  // first row of tile t (VECTOR mode) and its misalignment
+    m0 = ((int)t / n_tiles) * kGemmBM;  // (fewer than 2^31 tiles: M < 2^31)
+    const int rpb = (int)p.ga_rows_per_batch;
+    const int bi = m0 / rpb;
+    const float* tb = p.gather_a + (int64_t)bi * p.ga_batch_stride + (int64_t)(m0 - bi * rpb) * p.ga_row_stride;
+    sh = vec_mode ? (int)((reinterpret_cast<uintptr_t>(tb) >> 2) & 3) : 0;
+    return tb;
+  };
   const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (threadIdx.x == 0) {
@@ -459,8 +522,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       bar_init(&full_b[s], 1);
       bar_init(&empty_b[s], 1);
     }
-    for (int s = 0; s < kPersAStages; ++s) {
-      bar_init(&empty_a[s], 1);
+    for (int s = 0; s < kPersRawStages; ++s) bar_init(&empty_raw[s], 1);
+    for (int s = 0; s < kPersLoStages; ++s) {
+      bar_init(&empty_lo[s], 1);
       bar_init(&conv_a[s], 2);  // one arrival per converter warp
     }
     for (int t = 0; t < 2; ++t) {
@@ -482,13 +546,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int64_t q = 0; q < my_tiles; ++q) {
         const int64_t t = blockIdx.x + q * gridDim.x;
         const int n0 = (int)(t % n_tiles) * kGemmBN;
+        int m0_unused, sh;
+        tile_rows(t, m0_unused, sh);
         for (int i = 0; i < num_kb; ++i, ++g) {
           const int s = g % kPersBStages;
-          bar_wait(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);
+          bar_wait_relaxed(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);
           unsigned char* st = b_base + (size_t)s * kPersBStageBytes;
           bar_expect_tx(&full_b[s], kPersBStageBytes);
-          tma_load_2d(st, &map_b_hi, i * kGemmBK, n0, &full_b[s]);
-          tma_load_2d(st + kTileBBytes, &map_b_lo, i * kGemmBK, n0, &full_b[s]);
+          tma_load_2d(st, &maps.hi[sh], i * kGemmBK, n0, &full_b[s]);
+          tma_load_2d(st + kTileBBytes, &maps.lo[sh], i * kGemmBK, n0, &full_b[s]);
         }
       }
     }
@@ -498,19 +564,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t g = 0, gch = 0;
       for (int64_t q = 0; q < my_tiles; ++q) {
         for (int i = 0; i < num_kb; ++i, ++g) {
-          const int sa = g % kPersAStages, sb = g % kPersBStages;
+          const int sr = g % kPersRawStages, sl = g % kPersLoStages, sb = g % kPersBStages;
           const int in_chunk = i % kGemmChunk;
           const int buf = gch & 1;
           if (in_chunk == 0 && gch >= 2) {  // the epilogue must have folded the chunk that used this accumulator (two chunks ago)
             bar_wait(&tmem_empty[buf], ((gch >> 1) - 1) & 1);
             tc_fence_after();
           }
-          bar_wait(&conv_a[sa], (g / kPersAStages) & 1);
+          bar_wait(&conv_a[sl], (g / kPersLoStages) & 1);
           bar_wait(&full_b[sb], (g / kPersBStages) & 1);
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(buf * kGemmBN);
-          const uint32_t sta = s32(a_base + (size_t)sa * kPersAStageBytes), stb = s32(b_base + (size_t)sb * kPersBStageBytes);
-          const uint64_t a_hi = make_sw128_desc(sta), a_lo = make_sw128_desc(sta + kTileABytes);
+          const uint32_t stb = s32(b_base + (size_t)sb * kPersBStageBytes);
+          const uint64_t a_hi = make_sw128_desc(s32(raw_base + (size_t)sr * kTileABytes));
+          const uint64_t a_lo = make_sw128_desc(s32(lo_base + (size_t)sl * kTileABytes));
           const uint64_t b_hi = make_sw128_desc(stb), b_lo = make_sw128_desc(stb + kTileBBytes);
 #pragma unroll
           for (int k = 0; k < kGemmBK / kUmmaK; ++k) {
@@ -519,7 +586,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             umma_tf32(acc, a_lo + adv, b_hi + adv, kIdesc, 1);
             umma_tf32(acc, a_hi + adv, b_hi + adv, kIdesc, 1);
           }
-          umma_commit(&empty_a[sa]);
+          umma_commit(&empty_raw[sr]);
+          umma_commit(&empty_lo[sl]);
           umma_commit(&empty_b[sb]);
           if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) {
             umma_commit(&tmem_full[buf]);
@@ -529,59 +597,124 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else if (warp < 4) {
-    // ===== 2 converter warps: gather the A tile of K-block g (4-byte cp.async, 64 rows per warp), derive its lo tile =====
+    // ===== 2 converter warps: gather the A tile of K-block g (64 rows per warp), derive its lo tile =====
+    // One warp executes a dependent instruction stream at ~0.2 IPC, so what bounds this role is its instruction COUNT per K-block:
+    // everything that does not change between K-blocks is hoisted (lane offsets, per-tile base / misalignment), shared memory is
+    // addressed through 32-bit shared-space addresses (LDS / STS / LDGSTS with immediate offsets), and the rare cases (first chunk of a
+    // misaligned row, partial tiles) live in their own branches.
     const int ct = threadIdx.x - 64;
     const uint32_t total_g = (uint32_t)(my_tiles * num_kb);
-    auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+    const int wrow0 = (warp - 2) * 64;
+    const uint32_t raw_s = s32(raw_base), lo_s = s32(lo_base);
+    // the issue cursor (tile, K-block) with the per-tile constants of its tile
+    int64_t is_t = blockIdx.x;
+    int is_i = 0, is_m0 = 0, is_sh = 0;
+    const float* is_base = p.gather_a;
+    if (my_tiles > 0) is_base = tile_rows(is_t, is_m0, is_sh);
+    // VECTOR mode: lane = (row within a group of 4, 16-byte chunk c of the 128-byte row segment); rows wrow0 + 8 j + rsub ("even") and
+    // wrow0 + 8 j + 4 + rsub ("odd") for j = 0..7; chunk c of row r sits at r * 128 + ((c ^ (r % 8)) << 4)
+    const int c = lane & 7, rsub = lane >> 3;
+    const uint32_t off_even = (uint32_t)(wrow0 + rsub) * 128u + ((uint32_t)(c ^ rsub) << 4);
+    const uint32_t off_odd = (uint32_t)(wrow0 + 4 + rsub) * 128u + ((uint32_t)(c ^ (4 + rsub)) << 4);
+    // 4-byte mode: lane = column of the K-block; element (r, lane) sits at r * 128 + sw[r % 8]
+    uint32_t sw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sw[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
+    const bool rows_regular = (p.ga_rows_per_batch % 64) == 0;  // a warp's 64 rows never straddle two batches
     auto issue_gather = [&](uint32_t g) {
-      const int s = g % kPersAStages;
-      bar_wait(&empty_a[s], ((g / kPersAStages) & 1) ^ 1);
-      const int64_t q = g / num_kb;
-      const int i = (int)(g - q * num_kb);
-      const int64_t t = blockIdx.x + q * gridDim.x;
-      const int m0 = (int)(t / n_tiles) * kGemmBM;
-      const uint32_t st_a = s32(a_base + (size_t)s * kPersAStageBytes);
-      const int kcol = i * kGemmBK + lane;
-      const bool k_ok = kcol < p.K;
-      const int wrow0 = (warp - 2) * 64;
-      const int m_first = m0 + wrow0;
-      int hrow = m_first % (int)p.ga_rows_per_batch;
-      const float* rowp = p.gather_a + (int64_t)(m_first / (int)p.ga_rows_per_batch) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
-      const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
+      const int s = g % kPersRawStages;
+      bar_wait(&empty_raw[s], ((g / kPersRawStages) & 1) ^ 1);
+      const uint32_t st_a = raw_s + (uint32_t)s * kTileABytes;
+      const int i = is_i, m0 = is_m0;
+      if (vec_mode) {
+        const int k_first = i * kGemmBK + 4 * c - is_sh;  // first element of this lane's chunk (16-byte aligned in memory)
+        if (k_first >= 0 && m0 + kGemmBM <= p.M) {
+          const uint32_t sz = (uint32_t)min(max(p.K - k_first, 0), 4) * 4u;  // bytes read; the rest of the 16 is zero-filled
+          const float* src = sz ? is_base + (int64_t)(wrow0 + rsub) * p.K + k_first : is_base - is_sh;  // (any aligned address if sz = 0)
+          const int64_t pitch4 = sz ? 4 * (int64_t)p.K : 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st_a + off_even + (uint32_t)j * 1024u), "l"(src + (2 * j) * pitch4),
+                         "r"(sz)
+                         : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st_a + off_odd + (uint32_t)j * 1024u),
+                         "l"(src + (2 * j + 1) * pitch4), "r"(sz)
+                         : "memory");
+          }
+        } else {
+          // the chunk in front of a misaligned row (K-block 0: its first sh floats are NOT this row's -- they are zeroed rather than
+          // left to the minibatch's zero fill, a NaN there would leak into the row), and the rows of a partial last tile
+#pragma unroll 1
+          for (int it = 0; it < 16; ++it) {
+            const int r = wrow0 + it * 4 + rsub;
+            const bool row_ok = m0 + r < p.M;
+            const uint32_t dst = st_a + (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4);
+            const float* src = is_base + (int64_t)r * p.K + k_first;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool ok = row_ok && (k_first + e >= 0) && (k_first + e < p.K);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4u * e), "l"(ok ? src + e : p.gather_a), "r"(ok ? 4 : 0)
+                           : "memory");
+            }
+          }
+        }
+      } else {
+        const int kcol = i * kGemmBK + lane;
+        const bool k_ok = kcol < p.K;
+        const int m_first = m0 + wrow0;
+        const uint32_t dst0 = st_a + (uint32_t)wrow0 * 128u;
+        const int rpb = (int)p.ga_rows_per_batch;
+        int hrow = m_first % rpb;
+        const float* rowp = p.gather_a + (int64_t)(m_first / rpb) * p.ga_batch_stride + (int64_t)hrow * p.ga_row_stride + kcol;
+        if (rows_regular && m_first + 64 <= p.M) {
+          const float* src = k_ok ? rowp : p.gather_a;
+          const int64_t pitch = k_ok ? p.ga_row_stride : 0;
+          const uint32_t sz = k_ok ? 4u : 0u;
+#pragma unroll
+          for (int it = 0; it < 64; ++it)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (uint32_t)it * 128u + sw[it & 7]), "l"(src + it * pitch), "r"(sz)
+                         : "memory");
+        } else {
+          const int64_t wrap = p.ga_batch_stride - p.ga_rows_per_batch * p.ga_row_stride;
 #pragma unroll 8
-      for (int it = 0; it < 64; ++it) {
-        const int r = wrow0 + it;
-        const bool ok = k_ok && (m0 + r < p.M);
-        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
-        const float* src = ok ? rowp : p.gather_a;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st_a + off), "l"(src), "r"(ok ? 4 : 0) : "memory");
-        rowp += p.ga_row_stride;
-        if (++hrow == (int)p.ga_rows_per_batch) {
-          hrow = 0;
-          rowp += wrap;
+          for (int it = 0; it < 64; ++it) {
+            const bool ok = k_ok && (m_first + it < p.M);
+            const float* src = ok ? rowp : p.gather_a;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (uint32_t)it * 128u + sw[it & 7]), "l"(src), "r"(ok ? 4 : 0)
+                         : "memory");
+            rowp += p.ga_row_stride;
+            if (++hrow == rpb) {
+              hrow = 0;
+              rowp += wrap;
+            }
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++is_i == num_kb) {  // the cursor moves on to the next tile of this CTA
+        is_i = 0;
+        is_t += gridDim.x;
+        if (is_t < total_tiles) is_base = tile_rows(is_t, is_m0, is_sh);
+      }
     };
     if (total_g > 0) issue_gather(0);
     if (total_g > 1) issue_gather(1);
+    if (total_g > 2) issue_gather(2);
     for (uint32_t g = 0; g < total_g; ++g) {
-      const int s = g % kPersAStages;
-      if (g + 1 < total_g) asm volatile("cp.async.wait_group 1;" ::: "memory");  // block g has landed (block g + 1 may be in flight)
+      const int sr = g % kPersRawStages, sl = g % kPersLoStages;
+      // block g has landed (blocks g + 1, g + 2 may still be in flight)
+      if (g + 2 < total_g) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else if (g + 1 < total_g) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, 64;" ::: "memory");  // ... and so have the other converter warp's rows
-      unsigned char* st = a_base + (size_t)s * kPersAStageBytes;
-      const float4* a_raw = reinterpret_cast<const float4*>(st);
-      float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
-#pragma unroll 4
-      for (int j = 0; j < (int)(kTileABytes / 16 / 64); ++j) {
-        const float4 v = a_raw[ct + 64 * j];
-        a_lo[ct + 64 * j] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
-      }
+      bar_wait(&empty_lo[sl], ((g / kPersLoStages) & 1) ^ 1);  // the MMAs of block g - 2 are done with this lo buffer
+      // lo = x - trunc_tf32(x), element-wise (every element keeps its swizzled position): 16 float4 per thread, all loads first
+      const uint32_t ra = raw_s + (uint32_t)sr * kTileABytes + (uint32_t)ct * 16u, la = lo_s + (uint32_t)sl * kTileABytes + (uint32_t)ct * 16u;
+      split_lo_tile<kTileABytes>(ra, la);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv_a[s])) : "memory");
-      if (g + 2 < total_g) issue_gather(g + 2);
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv_a[sl])) : "memory");
+      if (g + 3 < total_g) issue_gather(g + 3);
     }
   } else {
     // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4 (tile row = quadrant * 32 + lane), column half = (warp - 4) / 4 =====
@@ -596,7 +729,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
       for (int ch = 0; ch < num_chunks; ++ch, ++gch) {
         const int buf = gch & 1;
-        bar_wait(&tmem_full[buf], (gch >> 1) & 1);
+        bar_wait_relaxed(&tmem_full[buf], (gch >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int g8 = 0; g8 < 8; ++g8) {
@@ -669,6 +802,29 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   hi[r * ldo + c] = h;
   lo[r * ldo + c] = v - h;
+}
+
+// lo[r][c] = x[r][c] - trunc_tf32(x[r][c])   (the pre-split lo copy of the B operand, pitch ldo)
+__global__ void __launch_bounds__(256) lo_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols, float* __restrict__ lo,
+                                                      int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ldo) return;
+  const int64_t r = i / ldo, c = i - r * ldo;
+  const float v = c < cols ? x[r * ldx + c] : 0.0f;
+  lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+}
+
+// the four shifted hi / lo copies of the minibatch (GatherMaps): hi[s][r][c] / lo[s][r][c] of x[r][c - s], zero for c - s outside [0, cols)
+__global__ void __launch_bounds__(256) split_shifted_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols, float* __restrict__ hi,
+                                                            float* __restrict__ lo, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * rows * ldo) return;
+  const int64_t s = i / (rows * ldo), rem = i - s * rows * ldo;
+  const int64_t r = rem / ldo, c = rem - r * ldo - s;
+  const float v = (c >= 0 && c < cols) ? x[r * ldx + c] : 0.0f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
 }
 
 // out[c, r] = (w ? w[r] : 1) * in[r, c]   (32 x 32 tiles through shared memory)
@@ -821,6 +977,13 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
     return e ? atoi(e) : 1;
   }();
   const bool convert = allow_convert && tma_ok(A, lda) && tma_ok(B, ldb);
+  static const int allow_b_lo = [] {
+    // =1: B's lo tile by TMA from a pre-split copy instead of the converter warps.  Measured: 8192^3 4.94 vs 5.05 ms, but 52 vs 44 us at
+    // the CMA-ES sizes (the extra pre-pass launch), and the K loop is bound by the 2-stage load latency either way -- off by default
+    const char* e = getenv("EVOK_GEMM_B_LO_TMA");
+    return e ? atoi(e) : 0;
+  }();
+  const bool b_lo_tma = convert && allow_b_lo;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if (convert) {
@@ -828,6 +991,12 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
     if ((rc = make_map(&mb_hi, B, N, K, ldb, kGemmBN))) return rc;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
+    if (b_lo_tma) {  // B's lo tile by TMA from a pre-split copy: the converter warps only derive A's (a third of the element-wise work)
+      float* b_lo = (float*)(w8 + g.off_b_lo);
+      lo_tf32_kernel<<<(unsigned)((N * g.ldk + 255) / 256), 256, 0, st>>>(B, ldb, N, K, b_lo, g.ldk);
+      EVOK_CHECK_LAUNCH();
+      if ((rc = make_map(&mb_lo, b_lo, N, K, g.ldk, kGemmBN))) return rc;
+    }
   } else {
     float* a_hi = (float*)(w8 + g.off_a_hi);
     float* a_lo = (float*)(w8 + g.off_a_lo);
@@ -861,6 +1030,7 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
   p.row_bias = nullptr;
   p.row_act = 0;
   p.debug = 0;
+  p.b_lo_tma = b_lo_tma ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
@@ -938,7 +1108,7 @@ extern "C" EVOK_API int evok_gemm_gather_rows(const float* params, int64_t batch
 
 extern "C" EVOK_API size_t evok_gemm_gather_rows_workspace_bytes(int64_t n_cols, int64_t K) {
   if (n_cols <= 0 || K <= 0) return 512;
-  return (size_t)2 * n_cols * round_up(K, 4) * sizeof(float) + 512;
+  return (size_t)8 * n_cols * round_up(K + 3, 4) * sizeof(float) + 512;  // 4 shifted copies of the hi and of the lo part
 }
 
 // The same product on the persistent kernel (gemm_gather_persistent_kernel): X is split into hi / lo copies in `ws` first (any
@@ -955,17 +1125,19 @@ extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t ba
     if (e && atoi(e) == 0 && tma_ok(X, ldx))
       return evok_gemm_gather_rows(params, batch_stride, w_offset, rows_per_batch, n_batches, X, ldx, n_cols, K, bias_offset, act, C, ldc, stream);
   }
-  const int64_t ldk = round_up(K, 4);
+  const int64_t ldk = round_up(K + 3, 4);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)2 * n_cols * ldk * sizeof(float)) return EVOK_E_WORKSPACE;
+  if (ws_bytes < (size_t)(base - (char*)ws) + (size_t)8 * n_cols * ldk * sizeof(float)) return EVOK_E_WORKSPACE;
   float* x_hi = reinterpret_cast<float*>(base);
-  float* x_lo = x_hi + n_cols * ldk;
-  split_tf32_kernel<<<(unsigned)((n_cols * K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n_cols, K, x_hi, x_lo, ldk);
+  float* x_lo = x_hi + 4 * n_cols * ldk;
+  split_shifted_kernel<<<(unsigned)((4 * n_cols * ldk + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n_cols, K, x_hi, x_lo, ldk);
   EVOK_CHECK_LAUNCH();
-  CUtensorMap mhi, mlo;
+  GatherMaps maps;
   int rc;
-  if ((rc = make_map(&mhi, x_hi, n_cols, K, ldk, kGemmBN))) return rc;
-  if ((rc = make_map(&mlo, x_lo, n_cols, K, ldk, kGemmBN))) return rc;
+  for (int s = 0; s < 4; ++s) {
+    if ((rc = make_map(&maps.hi[s], x_hi + s * n_cols * ldk, n_cols, ldk, ldk, kGemmBN))) return rc;
+    if ((rc = make_map(&maps.lo[s], x_lo + s * n_cols * ldk, n_cols, ldk, ldk, kGemmBN))) return rc;
+  }
   GemmParams p{};
   p.M = (int)M; p.N = (int)n_cols; p.K = (int)K;
   p.kblocks_per_split = (int)((K + kGemmBK - 1) / kGemmBK);
@@ -990,7 +1162,7 @@ extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t ba
   }
   const int64_t tiles = ((M + kGemmBM - 1) / kGemmBM) * ((n_cols + kGemmBN - 1) / kGemmBN);
   const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-  gemm_gather_persistent_kernel<<<grid, kGemmThreads, kPersSmemBytes, (cudaStream_t)stream>>>(mhi, mlo, p);
+  gemm_gather_persistent_kernel<<<grid, kGemmThreads, kPersSmemBytes, (cudaStream_t)stream>>>(maps, p);
   EVOK_CHECK_LAUNCH();
   return 0;
 }

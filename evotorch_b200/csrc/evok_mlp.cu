@@ -251,7 +251,7 @@ constexpr int kTail2MaxOut = 32;
 // accumulation over a quarter of the hidden units starts while the other quarters are still in flight.  Thread = (sample pair,
 // output group): per hidden unit two activation reads and one or two 16-byte broadcast weight reads serve 2 x OG FMAs.  96 KB of
 // shared memory per CTA: two CTAs per SM cover each other's fill latency.
-constexpr int kTail2Threads = 128;
+constexpr int kTail2Threads = 256;  // 8 warps = 4 output groups x 2 halves of the hidden units of each quarter
 constexpr int kTail2Samples = 64;   // samples per pass
 constexpr int kTail2Groups = 4;     // output groups (one warp each)
 constexpr int kTail2Slots = 8;      // padded outputs per group: weights of hidden unit h, group g at wsm[(h * 4 + g) * 8 ..]
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kTail2Threads)
   float* tile = tail_smem;                                                  // [h1][64]
   float* wsm = tile + (size_t)h1 * kTail2Samples;                           // [h1][4][8]
   float* bsm = wsm + (size_t)h1 * kTail2Groups * kTail2Slots;               // [32]
+  float* red = bsm + kTail2Groups * kTail2Slots;                            // [128][2 * OG] partial sums of the second half
   const float* W = params + (net + n_first) * ldp + spec.w_off[1];
   for (int e = threadIdx.x; e < h1 * kTail2Groups * kTail2Slots; e += kTail2Threads) wsm[e] = 0.0f;
   if (threadIdx.x < kTail2Groups * kTail2Slots) bsm[threadIdx.x] = 0.0f;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kTail2Threads)
   }
   if (threadIdx.x < dout) bsm[(threadIdx.x / OG) * kTail2Slots + threadIdx.x % OG] = __ldg(W + h1 * dout + threadIdx.x);
   const float* hrow = hid + net * h1 * ldh;
-  const int sp = threadIdx.x & 31, og = threadIdx.x >> 5;
+  const int sp = threadIdx.x & 31, og = (threadIdx.x >> 5) & 3, hh = threadIdx.x >> 7;
   const int hq = (h1 + 3) / 4;  // hidden units per commit group
   for (int64_t b0 = 0; b0 < B; b0 += kTail2Samples) {
     const int vec = (int)((ldh - b0 < kTail2Samples ? ldh - b0 : kTail2Samples) / 4);  // 16-byte pieces per row (ldh is a multiple of 4)
@@ -307,22 +308,27 @@ __global__ void __launch_bounds__(kTail2Threads)
       else if (q == 2) cp_async_wait<1>();
       else cp_async_wait<0>();
       const int ha = q * hq, hb = (ha + hq < h1) ? ha + hq : h1;
-      // act_0 in place, on the pieces this thread copied (its own cp.async writes are visible to it after the wait)
-      for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
-        const int h = e >> 4, v = e & 15;
-        if (v < vec) {
-          float4* p4 = reinterpret_cast<float4*>(tile + h * kTail2Samples + v * 4);
-          float4 t = *p4;
-          t.x = activate_fast(t.x, spec.acts[0]);
-          t.y = activate_fast(t.y, spec.acts[0]);
-          t.z = activate_fast(t.z, spec.acts[0]);
-          t.w = activate_fast(t.w, spec.acts[0]);
-          *p4 = t;
+      // act_0 in place, on the pieces this thread copied (its own cp.async writes are visible to it after the wait); nothing to do
+      // when the producer (the GEMM epilogue) has already applied it
+      if (spec.acts[0] != EVOK_ACT_NONE) {
+        for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
+          const int h = e >> 4, v = e & 15;
+          if (v < vec) {
+            float4* p4 = reinterpret_cast<float4*>(tile + h * kTail2Samples + v * 4);
+            float4 t = *p4;
+            t.x = activate_fast(t.x, spec.acts[0]);
+            t.y = activate_fast(t.y, spec.acts[0]);
+            t.z = activate_fast(t.z, spec.acts[0]);
+            t.w = activate_fast(t.w, spec.acts[0]);
+            *p4 = t;
+          }
         }
       }
       __syncthreads();
+      const int hmid = ha + (hb - ha + 1) / 2;
+      const int h_lo = hh ? hmid : ha, h_hi = hh ? hb : hmid;  // this warp's half of the quarter
 #pragma unroll 4
-      for (int h = ha; h < hb; ++h) {
+      for (int h = h_lo; h < h_hi; ++h) {
         const float xa = tile[h * kTail2Samples + sp], xb = tile[h * kTail2Samples + 32 + sp];
         const float4 w0 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots);
         float w[8] = {w0.x, w0.y, w0.z, w0.w, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -337,14 +343,23 @@ __global__ void __launch_bounds__(kTail2Threads)
         }
       }
     }
-    const int64_t ba = b0 + sp, bb = b0 + 32 + sp;
+    // the second half hands its partial sums to the first through shared memory
+    float* my_red = red + ((og * 32 + sp) * 2) * OG;
+    if (hh) {
 #pragma unroll
-    for (int j = 0; j < OG; ++j) {
-      const int o = og * OG + j;
-      if (o < dout) {
-        const float bias = bsm[og * kTail2Slots + j];
-        if (ba < B) out[(net * B + ba) * dout + o] = activate_fast(acca[j] + bias, spec.acts[1]);
-        if (bb < B) out[(net * B + bb) * dout + o] = activate_fast(accb[j] + bias, spec.acts[1]);
+      for (int j = 0; j < OG; ++j) my_red[j] = acca[j], my_red[OG + j] = accb[j];
+    }
+    __syncthreads();
+    if (!hh) {
+      const int64_t ba = b0 + sp, bb = b0 + 32 + sp;
+#pragma unroll
+      for (int j = 0; j < OG; ++j) {
+        const int o = og * OG + j;
+        if (o < dout) {
+          const float bias = bsm[og * kTail2Slots + j];
+          if (ba < B) out[(net * B + ba) * dout + o] = activate_fast(acca[j] + my_red[j] + bias, spec.acts[1]);
+          if (bb < B) out[(net * B + bb) * dout + o] = activate_fast(accb[j] + my_red[OG + j] + bias, spec.acts[1]);
+        }
       }
     }
   }
@@ -424,9 +439,9 @@ extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp
     int rc = evok_gemm_gather_rows_ws(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0],
                                       spec.w_off[0] + (int64_t)spec.dims[0] * h1, spec.acts[0], hid, ldh, gws, gws_bytes, stream);
     if (rc) return rc;
-    const size_t smem2 = ((size_t)h1 * kTail2Samples + (size_t)h1 * kTail2Groups * kTail2Slots + kTail2Groups * kTail2Slots) * sizeof(float);
+    const size_t smem2 = ((size_t)h1 * kTail2Samples + (size_t)h1 * kTail2Groups * kTail2Slots + kTail2Groups * kTail2Slots + 128 * 2 * 8) * sizeof(float);
     if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut && smem2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(hid) & 15) == 0) {
-      // 4 output groups (one warp each) x 32 sample pairs = 128 threads; outputs per thread = ceil(dout / 4)
+      // 4 output groups x 32 sample pairs x 2 halves of the hidden units = 256 threads; outputs per thread = ceil(dout / 4)
       const int og = (spec.dims[2] + kTail2Groups - 1) / kTail2Groups;
 #define EVOK_LAUNCH_TAIL2(OGV)                                                                                                      \
   do {                                                                                                                              \

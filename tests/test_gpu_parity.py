@@ -593,9 +593,15 @@ def test_shared_minibatch_forward_matches_float64_and_vmap(dims, acts, n, B):
     assert float((y.double() - h).abs().max()) <= 2e-5 * max(scale, 1.0)
     ref = torch.vmap(pol._call_one, in_dims=(0, None))(P, x)
     assert float((y - ref).abs().max()) <= 2e-5 * max(scale, 1.0)
-    # a padded (strided) population and a strided batch give the same bits
-    wideP = torch.zeros(n, pol.parameter_length + 3, device=DEV)
-    wideP[:, :pol.parameter_length] = P
-    widex = torch.zeros(B, dims[0] + 5, device=DEV)
-    widex[:, :dims[0]] = x
-    assert torch.equal(pol.forward_shared(wideP[:, :pol.parameter_length], widex[:, :dims[0]]), y)
+    # a padded (strided) population and a strided batch: the same networks at other alignments.  The K axis of a tile is cut at the
+    # 16-byte boundaries of ITS rows, so the summation order -- not the result beyond rounding -- depends on the alignment; junk in
+    # the padding (NaN) must not leak into any row
+    for pad in (1, 2, 3, 4):
+        wideP = torch.full((n, pol.parameter_length + pad), float("nan"), device=DEV)
+        wideP[:, :pol.parameter_length] = P
+        widex = torch.full((B, dims[0] + 5), float("nan"), device=DEV)
+        widex[:, :dims[0]] = x
+        y2 = pol.forward_shared(wideP[:, :pol.parameter_length], widex[:, :dims[0]])
+        assert float((y2 - y).abs().max()) <= 2e-5 * max(scale, 1.0)
+    # the same call twice gives the same bits
+    assert torch.equal(pol.forward_shared(P, x), y)
