@@ -98,5 +98,41 @@ for gen in range(3):
     ops.grad_push(ops.GRAD_SYMMETRIC, None, w, mu, sg, scale_mu=1.0, scale_sigma=1.0, peer=px, seed=3, stream_id=gen, row0=0)
     px.reduce_gradients()
 assert not px.timed_out()
+# ---- round-2 kernels
+# peer push / sharded ranking on one rank (local "peers")
+px.push_fitness(0, n)
+px.wait_fitness()
+# shared-minibatch policy forward: persistent gather GEMM (16-byte path at every row alignment, 4-byte path, generic tail) + tail kernels
+from evotorch_b200.neuroevolution import Policy  # noqa: E402
+
+for dims, acts, nn_, B in (((376, 256, 17), ("tanh", "none"), 5, 70), ((8, 512, 2), ("none", "tanh"), 3, 300), ((6, 16, 3), ("relu", "none"), 9, 33),
+                           ((33, 40, 24, 5), ("tanh", "sigmoid", "none"), 7, 31)):
+    layers = []
+    for l in range(len(acts)):
+        layers.append(torch.nn.Linear(dims[l], dims[l + 1]))
+        if acts[l] != "none":
+            layers.append({"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU, "sigmoid": torch.nn.Sigmoid}[acts[l]]())
+    pol = Policy(torch.nn.Sequential(*layers).to(dev))
+    for pad in (0, 1, 2, 3):
+        P = torch.randn(nn_, pol.parameter_length + pad, device=dev)[:, :pol.parameter_length]
+        pol.forward_shared(P, torch.randn(B, dims[0] + pad, device=dev)[:, :dims[0]])
+# CMA-ES glue, SYRK with the fused covariance update, Cholesky, batched functional kernels
+c = CMAES(Problem("min", sphere, initial_bounds=(-3, 3), solution_length=72, device=dev, seed=1), stdev_init=1.0, popsize=40)
+c.run(3)
+c.enable_cuda_graph()
+c.run(3)
+for nch in (1, 5, 64, 65, 200):
+    Bm = torch.randn(nch, nch, device=dev)
+    ops.cholesky((Bm @ Bm.T / nch + torch.eye(nch, device=dev)).contiguous())
+from evotorch_b200.algorithms.functional import cem, cem_ask, cem_tell, pgpe, pgpe_ask, pgpe_tell  # noqa: E402
+
+st = pgpe(center_init=torch.randn(3, 21, device=dev), center_learning_rate=0.3, stdev_learning_rate=0.1, objective_sense="min", stdev_init=1.0)
+for _ in range(2):
+    pop = pgpe_ask(st, popsize=10)
+    st = pgpe_tell(st, pop, (pop * pop).sum(-1))
+st = cem(center_init=torch.randn(3, 21, device=dev), parenthood_ratio=0.5, objective_sense="min", stdev_init=1.0)
+for _ in range(2):
+    pop = cem_ask(st, popsize=10)
+    st = cem_tell(st, pop, (pop * pop).sum(-1))
 torch.cuda.synchronize()
 print("SANITIZE_RUN_COMPLETE")
