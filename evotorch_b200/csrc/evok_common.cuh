@@ -255,6 +255,13 @@ __device__ __forceinline__ float tanh_1e6(float x) {
   }
   return copysignf(r, x);
 }
+// branch-free tanh = (1 - e) / (1 + e), e = exp(-2 |x|), with the hardware ex2 / rcp: 7 instructions, absolute error ~1e-7 (the RELATIVE
+// error grows towards x = 0, where 1 - e cancels: use tanh_1e6 where that matters).  For the GEMM epilogue of the policy forward, where
+// 128 activations per thread sit on the critical path of every tile.
+__device__ __forceinline__ float tanh_abs1e7(float x) {
+  const float e = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
 __device__ __forceinline__ float activate_fast(float v, int act) {
   switch (act) {
     case EVOK_ACT_TANH: return tanh_1e6(v);

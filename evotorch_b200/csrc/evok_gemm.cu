@@ -189,7 +189,19 @@ struct GemmParams {
   int row_act;
   int debug;  // measurement only (EVOK_GATHER_DEBUG): 1 = skip the global loads of the gather, 2 = skip bias / activation
   int b_lo_tma;  // CONVERT: the lo tile of B comes from a pre-split copy (map_b_lo) instead of being derived by the converter warps
+  long long* trace;  // -DEVOK_GEMM_TRACE builds only: clock64() stamps of CTA 0's roles per K-block (scripts/gather_trace.py)
 };
+
+#ifdef EVOK_GEMM_TRACE
+#define EVOK_TRACE(slot, idx)                                                                                      \
+  do {                                                                                                             \
+    if (p.trace && blockIdx.x == 0 && (idx) < 512u) p.trace[(size_t)(idx) * 16 + (slot)] = clock64();               \
+  } while (0)
+#else
+#define EVOK_TRACE(slot, idx) \
+  do {                        \
+  } while (0)
+#endif
 
 // The tensor core adds every MMA into the TMEM accumulator with round-toward-zero; over hundreds of MMAs that is a
 // systematic shrink of ~2e-8 per MMA (measured: -7e-6 relative after 384 MMAs).  The accumulation is therefore CHUNKED:
@@ -551,10 +563,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int i = 0; i < num_kb; ++i, ++g) {
           const int s = g % kPersBStages;
           bar_wait_relaxed(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);
+          EVOK_TRACE(9, g);
           unsigned char* st = b_base + (size_t)s * kPersBStageBytes;
-          bar_expect_tx(&full_b[s], kPersBStageBytes);
+          // (p.debug == 3, measurement only: the lo tile of the minibatch is not loaded -- wrong results, half the L2 -> SM traffic)
+          bar_expect_tx(&full_b[s], p.debug == 3 ? kTileBBytes : kPersBStageBytes);
           tma_load_2d(st, &maps.hi[sh], i * kGemmBK, n0, &full_b[s]);
-          tma_load_2d(st + kTileBBytes, &maps.lo[sh], i * kGemmBK, n0, &full_b[s]);
+          if (p.debug != 3) tma_load_2d(st + kTileBBytes, &maps.lo[sh], i * kGemmBK, n0, &full_b[s]);
         }
       }
     }
@@ -572,7 +586,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             tc_fence_after();
           }
           bar_wait(&conv_a[sl], (g / kPersLoStages) & 1);
+          EVOK_TRACE(6, g);
           bar_wait(&full_b[sb], (g / kPersBStages) & 1);
+          EVOK_TRACE(7, g);
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(buf * kGemmBN);
           const uint32_t stb = s32(b_base + (size_t)sb * kPersBStageBytes);
@@ -589,6 +605,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           umma_commit(&empty_raw[sr]);
           umma_commit(&empty_lo[sl]);
           umma_commit(&empty_b[sb]);
+          EVOK_TRACE(8, g);
           if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) {
             umma_commit(&tmem_full[buf]);
             ++gch;
@@ -624,6 +641,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     auto issue_gather = [&](uint32_t g) {
       const int s = g % kPersRawStages;
       bar_wait(&empty_raw[s], ((g / kPersRawStages) & 1) ^ 1);
+      if (threadIdx.x == 64) EVOK_TRACE(4, g);
       const uint32_t st_a = raw_s + (uint32_t)s * kTileABytes;
       const int i = is_i, m0 = is_m0;
       if (vec_mode) {
@@ -702,19 +720,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (total_g > 2) issue_gather(2);
     for (uint32_t g = 0; g < total_g; ++g) {
       const int sr = g % kPersRawStages, sl = g % kPersLoStages;
+      if (threadIdx.x == 64) EVOK_TRACE(0, g);
       // block g has landed (blocks g + 1, g + 2 may still be in flight)
       if (g + 2 < total_g) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else if (g + 1 < total_g) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (threadIdx.x == 64) EVOK_TRACE(14, g);
       asm volatile("bar.sync 1, 64;" ::: "memory");  // ... and so have the other converter warp's rows
+      if (threadIdx.x == 64) EVOK_TRACE(1, g);
       bar_wait(&empty_lo[sl], ((g / kPersLoStages) & 1) ^ 1);  // the MMAs of block g - 2 are done with this lo buffer
+      if (threadIdx.x == 64) EVOK_TRACE(2, g);
       // lo = x - trunc_tf32(x), element-wise (every element keeps its swizzled position): 16 float4 per thread, all loads first
       const uint32_t ra = raw_s + (uint32_t)sr * kTileABytes + (uint32_t)ct * 16u, la = lo_s + (uint32_t)sl * kTileABytes + (uint32_t)ct * 16u;
       split_lo_tile<kTileABytes>(ra, la);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv_a[sl])) : "memory");
+      if (threadIdx.x == 64) EVOK_TRACE(3, g);
       if (g + 3 < total_g) issue_gather(g + 3);
+      if (threadIdx.x == 64) EVOK_TRACE(5, g);
     }
   } else {
     // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4 (tile row = quadrant * 32 + lane), column half = (warp - 4) / 4 =====
@@ -729,7 +753,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
       for (int ch = 0; ch < num_chunks; ++ch, ++gch) {
         const int buf = gch & 1;
+        if (threadIdx.x == 128) EVOK_TRACE(10, gch);
         bar_wait_relaxed(&tmem_full[buf], (gch >> 1) & 1);
+        if (threadIdx.x == 128) EVOK_TRACE(11, gch);
         tc_fence_after();
 #pragma unroll
         for (int g8 = 0; g8 < 8; ++g8) {
@@ -741,6 +767,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
+        if (threadIdx.x == 128) EVOK_TRACE(12, gch);
       }
       const int64_t m = (int64_t)m0 + quad * 32 + lane;
       if (m < p.M) {
@@ -774,7 +801,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         } else if (p.row_act == EVOK_ACT_TANH) {
 #pragma unroll
           for (int j = 0; j < kGemmBN / 2; j += 4)
-            store4(j, tanh_1e6(acc[j] + b), tanh_1e6(acc[j + 1] + b), tanh_1e6(acc[j + 2] + b), tanh_1e6(acc[j + 3] + b));
+            store4(j, tanh_abs1e7(acc[j] + b), tanh_abs1e7(acc[j + 1] + b), tanh_abs1e7(acc[j + 2] + b), tanh_abs1e7(acc[j + 3] + b));
         } else {
 #pragma unroll
           for (int j = 0; j < kGemmBN / 2; j += 4)
@@ -1031,6 +1058,7 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
   p.row_act = 0;
   p.debug = 0;
   p.b_lo_tma = b_lo_tma ? 1 : 0;
+  p.trace = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
@@ -1150,6 +1178,16 @@ extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t ba
   p.row_bias = bias_offset >= 0 ? params + bias_offset : nullptr;
   p.rb_batch_stride = batch_stride;
   p.row_act = act;
+  {
+    const char* e = getenv("EVOK_GATHER_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
+#ifdef EVOK_GEMM_TRACE
+  {
+    const char* e = getenv("EVOK_GATHER_TRACE_PTR");  // device pointer (hex) of a 512 x 16 int64 buffer
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+#endif
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
