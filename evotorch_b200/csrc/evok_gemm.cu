@@ -195,7 +195,7 @@ struct GemmParams {
 #ifdef EVOK_GEMM_TRACE
 #define EVOK_TRACE(slot, idx)                                                                                      \
   do {                                                                                                             \
-    if (p.trace && blockIdx.x == 0 && (idx) < 512u) p.trace[(size_t)(idx) * 16 + (slot)] = clock64();               \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 512u) p.trace[(size_t)(idx) * 16 + (slot)] = clock64();               \
   } while (0)
 #else
 #define EVOK_TRACE(slot, idx) \
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int kb_end = min(total_kb, kb_begin + p.kblocks_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
   const int num_chunks = (num_kb + kGemmChunk - 1) / kGemmChunk;
+  if (threadIdx.x == 0) EVOK_TRACE(13, 0u);  // kernel start
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const int s = i % kGemmStages;
         const uint32_t use = i / kGemmStages;
         bar_wait_relaxed(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
+        EVOK_TRACE(9, (uint32_t)i);
         unsigned char* st = base + (size_t)s * kStageBytes;
         bar_expect_tx(&full[s], (GATHER ? kTileBBytes : (CONVERT ? kTileABytes + kTileBBytes : kStageBytes)) + ((CONVERT && p.b_lo_tma) ? kTileBBytes : 0u));
         const int kx = (kb_begin + i) * kGemmBK;
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           tc_fence_after();
         }
         bar_wait(CONVERT ? &conv[s] : &full[s], use & 1);  // CONVERT: the converter warps have derived the lo tiles of this stage
+        EVOK_TRACE(6, (uint32_t)i);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * kGemmBN);
         const uint32_t st = s32(base + (size_t)s * kStageBytes);
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         umma_commit(&empty[s]);  // stage reusable once these MMAs have consumed it
         if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) umma_commit(&tmem_full[buf]);  // chunk accumulator complete
+        EVOK_TRACE(8, (uint32_t)i);
       }
     }
   } else if (warp < 4) {
@@ -352,7 +356,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's copies of block i have landed
           asm volatile("bar.sync 1, 64;" ::: "memory");         // ... and so have the other converter warp's
         }
+        if (threadIdx.x == 64) EVOK_TRACE(0, (uint32_t)i);
         bar_wait(&full[s], use & 1);
+        if (threadIdx.x == 64) EVOK_TRACE(1, (uint32_t)i);
         const float4* a_raw = reinterpret_cast<const float4*>(st);
         float4* a_lo = reinterpret_cast<float4*>(st + kTileABytes);
         const float4* b_raw = reinterpret_cast<const float4*>(st + 2 * kTileABytes);
@@ -364,6 +370,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&conv[s])) : "memory");
+        if (threadIdx.x == 64) EVOK_TRACE(3, (uint32_t)i);
         // the next block's copy is issued AFTER this block has been handed to the tensor core (its stage frees up when the MMAs of
         // block i - 1 retire, which overlaps with the MMAs of block i)
         if (GATHER && i + 1 < num_kb) issue_gather(i + 1);
@@ -380,7 +387,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int j = 0; j < kGemmBN / 2; ++j) acc[j] = 0.0f;
     auto fold_chunk = [&](int ch) {
       const int buf = ch & 1;
+      if (threadIdx.x == 128) EVOK_TRACE(10, (uint32_t)ch);
       bar_wait_relaxed(&tmem_full[buf], (ch >> 1) & 1);
+      if (threadIdx.x == 128) EVOK_TRACE(11, (uint32_t)ch);
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -394,6 +403,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&tmem_empty[buf])) : "memory");
     };
     for (int ch = 0; ch < num_chunks; ++ch) fold_chunk(ch);
+    if (threadIdx.x == 128) EVOK_TRACE(13, 1u);  // all chunks folded: the store phase starts
     if (GATHER && p.row_bias && p.debug != 2) {  // C = act(acc + bias of this row): TMEM lane = row of the tile
       const int64_t m = (int64_t)m0 + quad * 32 + lane;
       if (m < p.M) {
@@ -459,6 +469,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       __syncwarp();
     }
   }
+  if (threadIdx.x == 128) EVOK_TRACE(13, 2u);  // stores issued
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -1059,6 +1070,12 @@ static int gemm_impl(const float* A, int64_t lda, const float* B, int64_t ldb, i
   p.debug = 0;
   p.b_lo_tma = b_lo_tma ? 1 : 0;
   p.trace = nullptr;
+#ifdef EVOK_GEMM_TRACE
+  {
+    const char* e = getenv("EVOK_GATHER_TRACE_PTR");
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes) != cudaSuccess ||
