@@ -497,6 +497,11 @@ struct GatherMaps {
   CUtensorMap lo[4];
 };
 
+// K-blocks per TMEM accumulator chunk, as in the generic kernel.  (6 -- two chunks per 12-block tile, so that the tensor core could finish
+// a whole tile while the epilogue stores the previous one -- was tried: 28.7 vs 29.0 ms, not worth the larger round-toward-zero error.
+// The timeline shows why: during the store phase the converter warps themselves slow down 3-5x -- the epilogue's row-per-thread 16-byte
+// stores are 32 cache-line operations per warp instruction, 8192 per tile, in the same LSU pipe as the converters' LDS / STS / LDGSTS.)
+constexpr int kPersChunk = 4;
 constexpr int kPersRawStages = 4, kPersLoStages = 2, kPersBStages = 2;
 constexpr uint32_t kPersBStageBytes = 2 * kTileBBytes;
 constexpr size_t kPersSmemBytes =
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   // whole kernel at 2.6 us per K-block against 0.9 us of tensor-core work.
   const bool vec_mode = (p.K % 4 == 0) && (p.ga_row_stride == p.K) && (p.ga_rows_per_batch % kGemmBM == 0);
   const int num_kb = (p.K + (vec_mode ? 3 : 0) + kGemmBK - 1) / kGemmBK;
-  const int num_chunks = (num_kb + kGemmChunk - 1) / kGemmChunk;
+  const int num_chunks = (num_kb + kPersChunk - 1) / kPersChunk;
   const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
   const int64_t total_tiles = (int64_t)((p.M + kGemmBM - 1) / kGemmBM) * n_tiles;
   auto tile_rows = [&](int64_t t, int& m0, int& sh) -> const float* {  // first row of tile t (VECTOR mode) and its misalignment
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int64_t q = 0; q < my_tiles; ++q) {
         for (int i = 0; i < num_kb; ++i, ++g) {
           const int sr = g % kPersRawStages, sl = g % kPersLoStages, sb = g % kPersBStages;
-          const int in_chunk = i % kGemmChunk;
+          const int in_chunk = i % kPersChunk;
           const int buf = gch & 1;
           if (in_chunk == 0 && gch >= 2) {  // the epilogue must have folded the chunk that used this accumulator (two chunks ago)
             bar_wait(&tmem_empty[buf], ((gch >> 1) - 1) & 1);
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           umma_commit(&empty_lo[sl]);
           umma_commit(&empty_b[sb]);
           EVOK_TRACE(8, g);
-          if (in_chunk == kGemmChunk - 1 || i == num_kb - 1) {
+          if (in_chunk == kPersChunk - 1 || i == num_kb - 1) {
             umma_commit(&tmem_full[buf]);
             ++gch;
           }
