@@ -62,7 +62,7 @@ _SIGNATURES = {
     "evok_mlp_forward_shared": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "evok_gemm_gather_rows": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P]),
     "evok_gemm_gather_rows_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "evok_gemm_gather_rows_ws": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P, c_size_t, _P]),
+    "evok_gemm_gather_rows_ws": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_size_t, _P]),
     "evok_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "evok_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "evok_gemm_nt_affine": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, c_size_t, _P]),

@@ -189,6 +189,7 @@ struct GemmParams {
   int row_act;
   int debug;  // measurement only (EVOK_GATHER_DEBUG): 1 = skip the global loads of the gather, 2 = skip bias / activation
   int b_lo_tma;  // CONVERT: the lo tile of B comes from a pre-split copy (map_b_lo) instead of being derived by the converter warps
+  int c_unit_fastest;  // persistent gather kernel: C[(batch * N + col) * rows_per_batch + row_in_batch] (one cache line per store instruction)
   long long* trace;  // -DEVOK_GEMM_TRACE builds only: clock64() stamps of CTA 0's roles per K-block (scripts/gather_trace.py)
 };
 
@@ -796,9 +797,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         // per-element switch would not fit the instruction cache)
         float* crow = p.C + m * p.ldc;
         const int col0 = n0 + half * (kGemmBN / 2);
+        // unit-fastest layout: the 32 lanes of a warp (consecutive rows of one batch) write 128 consecutive bytes per instruction
+        const int64_t bi_c = m / p.ga_rows_per_batch;
+        float* ccol = p.C + (bi_c * p.N + col0) * p.ga_rows_per_batch + (m - bi_c * p.ga_rows_per_batch);
+        const int64_t cstride = p.ga_rows_per_batch;
         auto store4 = [&](int j, float v0, float v1, float v2, float v3) {
           const int col = col0 + j;
-          if (vec_ok && col + 4 <= p.N) {
+          if (p.c_unit_fastest) {
+            const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (col + u < p.N) ccol[(int64_t)(j + u) * cstride] = v[u];
+          } else if (vec_ok && col + 4 <= p.N) {
             *reinterpret_cast<float4*>(crow + col) = make_float4(v0, v1, v2, v3);
           } else {
             const float v[4] = {v0, v1, v2, v3};
@@ -1162,17 +1172,20 @@ extern "C" EVOK_API size_t evok_gemm_gather_rows_workspace_bytes(int64_t n_cols,
 }
 
 // The same product on the persistent kernel (gemm_gather_persistent_kernel): X is split into hi / lo copies in `ws` first (any
-// alignment / pitch of X is fine).  EVOK_GATHER_PERSISTENT=0 routes to the one-tile-per-CTA kernel instead (measurement only).
+// alignment / pitch of X is fine).  unit_fastest = 1 writes C[(batch * n_cols + col) * rows_per_batch + row] instead of the row-major
+// C[(batch * rows_per_batch + row) * ldc + col]: one cache line per store instruction of the epilogue instead of 32.
+// EVOK_GATHER_PERSISTENT=0 routes the row-major case to the one-tile-per-CTA kernel instead (measurement only).
 extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch,
                                                  int64_t n_batches, const float* X, int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset,
-                                                 int act, float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+                                                 int act, float* C, int64_t ldc, int unit_fastest, void* ws, size_t ws_bytes, void* stream) {
   if (!params || !X || !C || !ws) return EVOK_E_NULLPTR;
   const int64_t M = rows_per_batch * n_batches;
-  if (rows_per_batch <= 0 || n_batches <= 0 || n_cols <= 0 || K <= 0 || ldx < K || ldc < n_cols || M >= (1ll << 31)) return EVOK_E_BADSIZE;
+  if (rows_per_batch <= 0 || n_batches <= 0 || n_cols <= 0 || K <= 0 || ldx < K || (!unit_fastest && ldc < n_cols) || M >= (1ll << 31))
+    return EVOK_E_BADSIZE;
   if (act < EVOK_ACT_NONE || act > EVOK_ACT_SIGMOID) return EVOK_E_BADENUM;
   {
     const char* e = getenv("EVOK_GATHER_PERSISTENT");
-    if (e && atoi(e) == 0 && tma_ok(X, ldx))
+    if (!unit_fastest && e && atoi(e) == 0 && tma_ok(X, ldx))
       return evok_gemm_gather_rows(params, batch_stride, w_offset, rows_per_batch, n_batches, X, ldx, n_cols, K, bias_offset, act, C, ldc, stream);
   }
   const int64_t ldk = round_up(K + 3, 4);
@@ -1200,6 +1213,7 @@ extern "C" EVOK_API int evok_gemm_gather_rows_ws(const float* params, int64_t ba
   p.row_bias = bias_offset >= 0 ? params + bias_offset : nullptr;
   p.rb_batch_stride = batch_stride;
   p.row_act = act;
+  p.c_unit_fastest = unit_fastest ? 1 : 0;
   {
     const char* e = getenv("EVOK_GATHER_DEBUG");
     p.debug = e ? atoi(e) : 0;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kMlpThreads)
 
 // ---- shared-minibatch forward (SupervisedNE with common_minibatch, supervisedne.py:337-347): layers 2..n of N networks on B samples.
 // The first layer is the tensor-core GEMM over the stacked weight rows (evok_gemm_gather_rows), which leaves
-//   hid[(i * H1 + h) * ldh + b] = act_0(W_0^i x_b + b_0^i)[h];
+//   hid[(i * B + b) * H1 + h] = act_0(W_0^i x_b + b_0^i)[h]      (unit fastest: one cache line per store instruction of the GEMM epilogue);
 // this kernel takes one (network i, tile of 32 samples) per CTA, keeps the tile's activations in shared memory ([width][33]) and runs
 // the remaining layers with fp32 FMAs: thread = (sample lane, output neuron), the weight row is a broadcast load shared by the 32
 // samples of the warp.  out[(i * B + b) * O + o].
@@ -198,7 +198,11 @@ __global__ void __launch_bounds__(kTailThreads)
   const bool b_ok = b < B;
   const float* prow = params + (net + n_first) * ldp;
   const int h1 = spec.dims[1];
-  for (int h = wid; h < h1; h += kTailThreads / 32) cur[h * pitch + lane] = b_ok ? activate_fast(hid[(net * h1 + h) * ldh + b], spec.acts[0]) : 0.0f;
+  // hid[(net * B + sample) * h1 + unit]: lanes over the units (coalesced), one sample of the tile per warp pass
+  for (int s = wid; s < kTailSamples; s += kTailThreads / 32) {
+    const int64_t bs = b0 + s;
+    for (int h = lane; h < h1; h += 32) cur[h * pitch + s] = bs < B ? activate_fast(hid[(net * B + bs) * h1 + h], spec.acts[0]) : 0.0f;
+  }
   for (int l = 1; l < spec.n_layers; ++l) {
     const int din = spec.dims[l], dout = spec.dims[l + 1];
     const float* W = prow + spec.w_off[l];
@@ -259,6 +263,9 @@ constexpr int kTail2Slots = 8;      // padded outputs per group: weights of hidd
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -270,8 +277,8 @@ __global__ void __launch_bounds__(kTail2Threads)
   extern __shared__ __align__(16) float tail_smem[];
   const int64_t net = blockIdx.x;
   const int h1 = spec.dims[1], dout = spec.dims[2];
-  float* tile = tail_smem;                                                  // [h1][64]
-  float* wsm = tile + (size_t)h1 * kTail2Samples;                           // [h1][4][8]
+  float* tile = tail_smem;                                                  // [64][h1 + 4]
+  float* wsm = tile + (size_t)(h1 + 4) * kTail2Samples;                     // [h1][4][8]
   float* bsm = wsm + (size_t)h1 * kTail2Groups * kTail2Slots;               // [32]
   float* red = bsm + kTail2Groups * kTail2Slots;                            // [128][2 * OG] partial sums of the second half
   const float* W = params + (net + n_first) * ldp + spec.w_off[1];
@@ -283,18 +290,22 @@ __global__ void __launch_bounds__(kTail2Threads)
     wsm[(h * kTail2Groups + o / OG) * kTail2Slots + o % OG] = __ldg(W + e);
   }
   if (threadIdx.x < dout) bsm[(threadIdx.x / OG) * kTail2Slots + threadIdx.x % OG] = __ldg(W + h1 * dout + threadIdx.x);
-  const float* hrow = hid + net * h1 * ldh;
   const int sp = threadIdx.x & 31, og = (threadIdx.x >> 5) & 3, hh = threadIdx.x >> 7;
-  const int hq = (h1 + 3) / 4;  // hidden units per commit group
+  const int hq = ((h1 + 15) / 16) * 4;  // hidden units per commit group (a multiple of 4; h1 % 4 == 0)
+  // The tile keeps the layout of hid -- [sample][unit], rows of h1 + 4 floats -- so it is filled with 16-byte copies; a thread reads FOUR
+  // consecutive units of its two samples per 16-byte load: with a row pitch of 4 (mod 32) floats the 8 lanes of a quarter warp cover all
+  // 32 banks exactly once.
+  const int pitch = h1 + 4;
+  const float* hnet = hid + net * B * h1;
+  const int c4 = h1 / 4;  // 16-byte pieces per row
   for (int64_t b0 = 0; b0 < B; b0 += kTail2Samples) {
-    const int vec = (int)((ldh - b0 < kTail2Samples ? ldh - b0 : kTail2Samples) / 4);  // 16-byte pieces per row (ldh is a multiple of 4)
     __syncthreads();  // weights staged / the previous pass is done with the tile
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int ha = q * hq, hb = (ha + hq < h1) ? ha + hq : h1;
-      for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
-        const int h = e >> 4, v = e & 15;
-        if (v < vec) cp_async_16(tile + h * kTail2Samples + v * 4, hrow + (int64_t)h * ldh + b0 + v * 4);
+      const int qa = q * hq / 4, qb = min((q + 1) * hq, h1) / 4, qn = max(qb - qa, 0);  // this quarter's pieces [qa, qb) of every row
+      for (int e = threadIdx.x; e < kTail2Samples * qn; e += kTail2Threads) {
+        const int b = e / qn, v4 = qa + (e - b * qn);
+        if (b0 + b < B) cp_async_16(tile + b * pitch + v4 * 4, hnet + (b0 + b) * h1 + v4 * 4);
       }
       cp_async_commit();
     }
@@ -307,14 +318,14 @@ __global__ void __launch_bounds__(kTail2Threads)
       else if (q == 1) cp_async_wait<2>();
       else if (q == 2) cp_async_wait<1>();
       else cp_async_wait<0>();
-      const int ha = q * hq, hb = (ha + hq < h1) ? ha + hq : h1;
+      const int qa = q * hq / 4, qb = min((q + 1) * hq, h1) / 4, qn = max(qb - qa, 0);
       // act_0 in place, on the pieces this thread copied (its own cp.async writes are visible to it after the wait); nothing to do
       // when the producer (the GEMM epilogue) has already applied it
       if (spec.acts[0] != EVOK_ACT_NONE) {
-        for (int e = ha * 16 + threadIdx.x; e < hb * 16; e += kTail2Threads) {
-          const int h = e >> 4, v = e & 15;
-          if (v < vec) {
-            float4* p4 = reinterpret_cast<float4*>(tile + h * kTail2Samples + v * 4);
+        for (int e = threadIdx.x; e < kTail2Samples * qn; e += kTail2Threads) {
+          const int b = e / qn, v4 = qa + (e - b * qn);
+          if (b0 + b < B) {
+            float4* p4 = reinterpret_cast<float4*>(tile + b * pitch + v4 * 4);
             float4 t = *p4;
             t.x = activate_fast(t.x, spec.acts[0]);
             t.y = activate_fast(t.y, spec.acts[0]);
@@ -325,21 +336,27 @@ __global__ void __launch_bounds__(kTail2Threads)
         }
       }
       __syncthreads();
-      const int hmid = ha + (hb - ha + 1) / 2;
-      const int h_lo = hh ? hmid : ha, h_hi = hh ? hb : hmid;  // this warp's half of the quarter
-#pragma unroll 4
-      for (int h = h_lo; h < h_hi; ++h) {
-        const float xa = tile[h * kTail2Samples + sp], xb = tile[h * kTail2Samples + 32 + sp];
-        const float4 w0 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots);
-        float w[8] = {w0.x, w0.y, w0.z, w0.w, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (OG > 4) {
-          const float4 w1 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots + 4);
-          w[4] = w1.x, w[5] = w1.y, w[6] = w1.z, w[7] = w1.w;
-        }
+      const int qmid = qa + (qn + 1) / 2;
+      const int v_lo = hh ? qmid : qa, v_hi = hh ? qb : qmid;  // this warp's half of the quarter (in 4-unit pieces)
+#pragma unroll 2
+      for (int v4 = v_lo; v4 < v_hi; ++v4) {
+        const float4 xa4 = *reinterpret_cast<const float4*>(tile + sp * pitch + v4 * 4);
+        const float4 xb4 = *reinterpret_cast<const float4*>(tile + (sp + 32) * pitch + v4 * 4);
+        const float xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w}, xb[4] = {xb4.x, xb4.y, xb4.z, xb4.w};
 #pragma unroll
-        for (int j = 0; j < OG; ++j) {
-          acca[j] = fmaf(w[j], xa, acca[j]);
-          accb[j] = fmaf(w[j], xb, accb[j]);
+        for (int u = 0; u < 4; ++u) {
+          const int h = v4 * 4 + u;
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots);
+          float w[8] = {w0.x, w0.y, w0.z, w0.w, 0.0f, 0.0f, 0.0f, 0.0f};
+          if (OG > 4) {
+            const float4 w1 = *reinterpret_cast<const float4*>(wsm + (h * kTail2Groups + og) * kTail2Slots + 4);
+            w[4] = w1.x, w[5] = w1.y, w[6] = w1.z, w[7] = w1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < OG; ++j) {
+            acca[j] = fmaf(w[j], xa[u], acca[j]);
+            accb[j] = fmaf(w[j], xb[u], accb[j]);
+          }
         }
       }
     }
@@ -437,10 +454,10 @@ extern "C" EVOK_API int evok_mlp_forward_shared(const float* params, int64_t ldp
     const int64_t c = (N - i0) < chunk ? (N - i0) : chunk;
     // layer 0 of the c networks as ONE stacked-rows tensor-core product: (c * H1 x in) * (in x B)
     int rc = evok_gemm_gather_rows_ws(params + i0 * ldp, ldp, spec.w_off[0], h1, c, X, ldx, B, spec.dims[0],
-                                      spec.w_off[0] + (int64_t)spec.dims[0] * h1, spec.acts[0], hid, ldh, gws, gws_bytes, stream);
+                                      spec.w_off[0] + (int64_t)spec.dims[0] * h1, spec.acts[0], hid, ldh, 1 /* unit fastest */, gws, gws_bytes, stream);
     if (rc) return rc;
-    const size_t smem2 = ((size_t)h1 * kTail2Samples + (size_t)h1 * kTail2Groups * kTail2Slots + kTail2Groups * kTail2Slots + 128 * 2 * 8) * sizeof(float);
-    if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut && smem2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(hid) & 15) == 0) {
+    const size_t smem2 = ((size_t)(h1 + 4) * kTail2Samples + (size_t)h1 * kTail2Groups * kTail2Slots + kTail2Groups * kTail2Slots + 128 * 2 * 8) * sizeof(float);
+    if (n_layers == 2 && spec.dims[2] <= kTail2MaxOut && smem2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(hid) & 15) == 0 && h1 % 4 == 0) {
       // 4 output groups x 32 sample pairs x 2 halves of the hidden units = 256 threads; outputs per thread = ceil(dout / 4)
       const int og = (spec.dims[2] + kTail2Groups - 1) / kTail2Groups;
 #define EVOK_LAUNCH_TAIL2(OGV)                                                                                                      \

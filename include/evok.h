@@ -220,11 +220,12 @@ int evok_mlp_forward_shared(const float* params, int64_t ldp, int64_t N, const f
 int evok_gemm_gather_rows(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch, int64_t n_batches, const float* X,
                           int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset, int act, float* C, int64_t ldc, void* stream);
 /* The same product on the PERSISTENT kernel (one CTA per SM walks the tiles; X pre-split into hi / lo copies in `ws`, so X may have any
- * alignment; epilogue overlapped with the next tile).  Used by evok_mlp_forward_shared. */
+ * alignment; epilogue overlapped with the next tile).  unit_fastest != 0: C[(batch * n_cols + col) * rows_per_batch + row] (ldc unused)
+ * instead of C[(batch * rows_per_batch + row) * ldc + col].  Used by evok_mlp_forward_shared. */
 size_t evok_gemm_gather_rows_workspace_bytes(int64_t n_cols, int64_t K);
 int evok_gemm_gather_rows_ws(const float* params, int64_t batch_stride, int64_t w_offset, int64_t rows_per_batch, int64_t n_batches, const float* X,
-                             int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset, int act, float* C, int64_t ldc, void* ws, size_t ws_bytes,
-                             void* stream);
+                             int64_t ldx, int64_t n_cols, int64_t K, int64_t bias_offset, int act, float* C, int64_t ldc, int unit_fastest, void* ws,
+                             size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6 / K7: fp32-accurate tensor-core GEMM (tcgen05 + TMEM + TMA, 3xTF32 operand splitting).

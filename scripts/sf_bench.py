@@ -5,6 +5,12 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
+import os
+
+import evotorch_b200._native as _nat
+
+if os.environ.get("SF_LIB"):  # A/B against a variant build (evotorch_b200/lib/libevok_<tag>.so)
+    _nat.LIB_PATH = os.environ["SF_LIB"]
 from evotorch_b200 import ops
 from evotorch_b200.neuroevolution import Policy
 
