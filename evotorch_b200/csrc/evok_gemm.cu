@@ -57,8 +57,7 @@ __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(s32(b)), "r"(parity) : "memory");
 }
-// The same wait for warps that are NOT on the critical path (the epilogue warps waiting for an accumulator chunk, the TMA producer
-// waiting for a free stage): sleep between polls.  A tight try_wait loop issues continuously, and eight spinning epilogue warps share
+// The same wait for warps that are NOT on the critical path (the epilogue warps waiting for an accumulator chunk): sleep between polls.  A tight try_wait loop issues continuously, and eight spinning epilogue warps share
 // the four schedulers with the two converter warps -- ncu showed the converters issue-starved at 0.13 IPC while the spin loops
 // executed more instructions than the rest of the kernel.
 __device__ __forceinline__ void bar_wait_relaxed(uint64_t* b, uint32_t parity) {
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kGemmStages;
         const uint32_t use = i / kGemmStages;
-        bar_wait_relaxed(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately
+        bar_wait(&empty[s], (use & 1) ^ 1);  // first use of a stage passes immediately (tight poll: with two stages the wake-up is on the critical path)
         EVOK_TRACE(9, (uint32_t)i);
         unsigned char* st = base + (size_t)s * kStageBytes;
         bar_expect_tx(&full[s], (GATHER ? kTileBBytes : (CONVERT ? kTileABytes + kTileBBytes : kStageBytes)) + ((CONVERT && p.b_lo_tma) ? kTileBBytes : 0u));
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         tile_rows(t, m0_unused, sh);
         for (int i = 0; i < num_kb; ++i, ++g) {
           const int s = g % kPersBStages;
-          bar_wait_relaxed(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);
+          bar_wait(&empty_b[s], ((g / kPersBStages) & 1) ^ 1);  // tight poll: the minibatch tile of block g + 2 is needed ~1 block later
           EVOK_TRACE(9, g);
           unsigned char* st = b_base + (size_t)s * kPersBStageBytes;
           // (p.debug == 3, measurement only: the lo tile of the minibatch is not loaded -- wrong results, half the L2 -> SM traffic)
